@@ -1,0 +1,147 @@
+// ORACLE -- test infrastructure, not product code.
+// C ABI used by tests / bench.py (ctypes) to drive the CPU oracle.
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "../fidget_b200/csrc/host/host_capi.h"
+#include "vm.h"
+
+using namespace oracle;
+
+struct fh_tape { fhost::TapeData d; };  // same layout as in host_capi.cc
+struct orc_tape { TapeP t; };
+
+static thread_local std::string g_err;
+#define ORC_TRY(body)                                                 \
+    try { body; return 0; }                                           \
+    catch (const std::exception& e) { g_err = e.what(); return -1; }  \
+    catch (...) { g_err = "unknown error"; return -1; }
+
+struct orc_stats {
+    uint64_t evaluated[8], filled_inside[8], filled_outside[8], ambiguous[8], simplified[8];
+    uint64_t pixels;
+};
+static void copy_stats(const TileStats& s, orc_stats* o) {
+    if (!o) return;
+    memcpy(o->evaluated, s.evaluated, sizeof o->evaluated);
+    memcpy(o->filled_inside, s.filled_inside, sizeof o->filled_inside);
+    memcpy(o->filled_outside, s.filled_outside, sizeof o->filled_outside);
+    memcpy(o->ambiguous, s.ambiguous, sizeof o->ambiguous);
+    memcpy(o->simplified, s.simplified, sizeof o->simplified);
+    o->pixels = s.pixels;
+}
+static Mat4 to_mat(const float* m16) {
+    Mat4 m;
+    memcpy(m.m, m16, sizeof m.m);
+    return m;
+}
+
+extern "C" {
+
+const char* orc_last_error(void) { return g_err.c_str(); }
+
+int32_t orc_tape_from_fh(const fh_tape* t, orc_tape** out) {
+    ORC_TRY(*out = new orc_tape{std::make_shared<const Tape>(t->d)});
+}
+void orc_tape_free(orc_tape* t) { delete t; }
+
+int32_t orc_tape_info(const orc_tape* t, uint32_t* asm_len, uint32_t* ssa_len, uint32_t* choice_count,
+                      uint32_t* slot_count, uint32_t* n_vars) {
+    ORC_TRY({
+        *asm_len = uint32_t(t->t->size());
+        *ssa_len = uint32_t(t->t->d.ssa.tape.size());
+        *choice_count = t->t->choice_count();
+        *slot_count = t->t->slot_count();
+        *n_vars = uint32_t(t->t->n_vars());
+    });
+}
+
+// vars: [n_vars][2] lower/upper; out: [n_out][2]; choices: [choice_count]
+int32_t orc_interval_eval(const orc_tape* t, const float* vars, float* out, uint8_t* choices,
+                          uint8_t* simplify) {
+    ORC_TRY({
+        IntervalEval e;
+        std::vector<Interval> v(t->t->n_vars());
+        for (size_t i = 0; i < v.size(); ++i) v[i] = Interval(vars[2 * i], vars[2 * i + 1]);
+        std::vector<Interval> o(t->t->d.ssa.output_count);
+        bool s = e.eval(*t->t, v.data(), o.data());
+        for (size_t i = 0; i < o.size(); ++i) { out[2 * i] = o[i].lo; out[2 * i + 1] = o[i].hi; }
+        if (choices) memcpy(choices, e.choices.data(), e.choices.size());
+        if (simplify) *simplify = s;
+    });
+}
+int32_t orc_point_eval(const orc_tape* t, const float* vars, float* out, uint8_t* choices, uint8_t* simplify) {
+    ORC_TRY({
+        PointEval e;
+        bool s = e.eval(*t->t, vars, out);
+        if (choices) memcpy(choices, e.choices.data(), e.choices.size());
+        if (simplify) *simplify = s;
+    });
+}
+int32_t orc_float_slice_eval(const orc_tape* t, const float* const* vars, float* const* out, uint64_t n) {
+    ORC_TRY({
+        FloatSliceEval e;
+        e.eval(*t->t, vars, size_t(n), out);
+    });
+}
+// grads are {v,dx,dy,dz} quadruples
+int32_t orc_grad_slice_eval(const orc_tape* t, const float* const* vars, float* const* out, uint64_t n) {
+    ORC_TRY({
+        GradSliceEval e;
+        e.eval(*t->t, reinterpret_cast<const Grad* const*>(vars), size_t(n), reinterpret_cast<Grad* const*>(out));
+    });
+}
+int32_t orc_simplify(const orc_tape* t, const uint8_t* choices, size_t n, orc_tape** out) {
+    ORC_TRY(*out = new orc_tape{simplify(*t->t, choices, n, t->t->d.n_regs)});
+}
+// Bytecode of an oracle tape (e.g. a simplified child), for feeding the GPU path
+int32_t orc_tape_bytecode(const orc_tape* t, int32_t repack, uint32_t* words, size_t cap, size_t* n_words,
+                          uint8_t* reg_count, uint32_t* mem_count) {
+    ORC_TRY({
+        fhost::Bytecode bc = fhost::make_bytecode(t->t->d.asm_, t->t->d.n_regs, repack != 0);
+        if (n_words) *n_words = bc.words.size();
+        if (reg_count) *reg_count = bc.reg_count;
+        if (mem_count) *mem_count = bc.mem_count;
+        if (words) {
+            if (cap < bc.words.size()) throw std::runtime_error("bytecode buffer too small");
+            memcpy(words, bc.words.data(), bc.words.size() * 4);
+        }
+    });
+}
+
+void orc_screen_to_world_2d(uint32_t w, uint32_t h, float* m16) { Mat4 m = screen_to_world_2d(w, h); memcpy(m16, m.m, 64); }
+void orc_screen_to_world_3d(uint32_t w, uint32_t h, uint32_t d, float* m16) { Mat4 m = screen_to_world_3d(w, h, d); memcpy(m16, m.m, 64); }
+void orc_pixel_mat(uint32_t w, uint32_t h, const float* wm9, float* m16) { Mat4 m = pixel_mat(w, h, wm9); memcpy(m16, m.m, 64); }
+void orc_mat4_mul(const float* a, const float* b, float* out) { Mat4 m = mat4_mul(to_mat(a), to_mat(b)); memcpy(out, m.m, 64); }
+void orc_transform_f32(const float* m16, float x, float y, float z, float* out3) { transform_f32(x, y, z, to_mat(m16), out3); }
+
+int32_t orc_render2d(const orc_tape* t, uint32_t w, uint32_t h, const float* mat16, float z, int32_t pixel_perfect,
+                     const uint32_t* tile_sizes, uint32_t n_tile_sizes, int32_t threads, uint32_t first_root,
+                     uint32_t n_roots, float* out, orc_stats* stats) {
+    ORC_TRY({
+        Render2DConfig cfg;
+        cfg.width = w; cfg.height = h; cfg.mat = to_mat(mat16); cfg.z = z;
+        cfg.pixel_perfect = pixel_perfect != 0;
+        if (n_tile_sizes) cfg.tile_sizes.assign(tile_sizes, tile_sizes + n_tile_sizes);
+        cfg.threads = threads; cfg.first_root = first_root; cfg.n_roots = n_roots;
+        TileStats s;
+        render2d(t->t, cfg, out, &s);
+        copy_stats(s, stats);
+    });
+}
+int32_t orc_render3d(const orc_tape* t, uint32_t w, uint32_t h, uint32_t d, const float* mat16,
+                     const uint32_t* tile_sizes, uint32_t n_tile_sizes, int32_t threads, uint32_t first_root,
+                     uint32_t n_roots, void* out, orc_stats* stats) {
+    ORC_TRY({
+        Render3DConfig cfg;
+        cfg.width = w; cfg.height = h; cfg.depth = d; cfg.mat = to_mat(mat16);
+        if (n_tile_sizes) cfg.tile_sizes.assign(tile_sizes, tile_sizes + n_tile_sizes);
+        cfg.threads = threads; cfg.first_root = first_root; cfg.n_roots = n_roots;
+        TileStats s;
+        render3d(t->t, cfg, reinterpret_cast<GeometryPixel*>(out), &s);
+        copy_stats(s, stats);
+    });
+}
+
+}  // extern "C"
