@@ -1,0 +1,694 @@
+// Host orchestration + C ABI of libfidget_cuda (include/fidget_cuda.h).
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../../include/fidget_cuda.h"
+#include "kernels.cuh"
+
+using namespace fdev;
+
+static thread_local std::string g_err;
+static int32_t fail(int32_t code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CU(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(FC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() { return static_cast<T*>(p); }
+};
+
+bool is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+}  // namespace
+
+struct fc_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    uint64_t arena_bytes = 1ull << 30;
+    // render scratch
+    DevBuf arena, jobs[MAX_LEVELS + 1], fills[MAX_LEVELS], choice_scratch, counters, stats, image, heightmap;
+    std::vector<cudaEvent_t> events;
+    std::mutex mu;
+};
+
+struct fc_tape {
+    fc_ctx* ctx = nullptr;
+    std::atomic<int> refs{1};
+    uint2* dev = nullptr;
+    std::vector<uint2> host;  // copy of the device clauses
+    fc_tape_info info{};
+    int ax[3] = {-1, -1, -1};  // input slots of X, Y, Z
+};
+
+struct fc_eval {
+    fc_ctx* ctx = nullptr;
+    DevBuf in, out, choices, simplify, ptrs, tmp;
+};
+
+////////////////////////////////////////////////////////////////////////////
+// bytecode <-> device clauses
+static int32_t transcode(const uint32_t* words, size_t n_words, uint8_t reg_count, uint32_t mem_count,
+                         uint32_t n_vars, uint32_t n_outputs, std::vector<uint2>& out, uint32_t& n_choices) {
+    if (!words || n_words < 4 || (n_words & 1)) return fail(FC_ERR_INVALID, "bytecode: bad length");
+    if (words[0] != 0xFFFFFFFFu || words[1] != 0u) return fail(FC_ERR_INVALID, "bytecode: missing start marker");
+    if (words[n_words - 2] != 0xFFFFFFFFu || words[n_words - 1] != 0xFFFFFFFFu)
+        return fail(FC_ERR_INVALID, "bytecode: missing end marker");
+    out.clear();
+    n_choices = 0;
+    auto reg_ok = [&](uint32_t r) { return r < reg_count; };
+    for (size_t i = 2; i + 2 < n_words; i += 2) {
+        uint32_t w = words[i], imm = words[i + 1];
+        uint32_t op = w & 0xff, b1 = (w >> 8) & 0xff, b2 = (w >> 16) & 0xff, b3 = w >> 24;
+        if (op >= OP_COUNT) return fail(FC_ERR_INVALID, "bytecode: unknown opcode " + std::to_string(op));
+        uint32_t x;
+        bool ok = true;
+        if (op == OP_OUTPUT) {
+            ok = reg_ok(b1) && imm < n_outputs;
+            x = enc(op, F_RR, 0xff, b1, 0xff);
+        } else if (op == OP_INPUT) {
+            ok = reg_ok(b1) && imm < n_vars;
+            x = enc(op, F_RR, b1, 0xff, 0xff);
+        } else if (op == OP_COPY) {
+            if (b2 == 0xff) { ok = reg_ok(b1); x = enc(op, F_RI, b1, 0xff, 0xff); }
+            else { ok = reg_ok(b1) && reg_ok(b2); x = enc(op, F_RR, b1, b2, 0xff); }
+        } else if (op_is_unary(op)) {
+            ok = reg_ok(b1) && reg_ok(b2);
+            x = enc(op, F_RR, b1, b2, 0xff);
+        } else if (op_is_binary(op)) {
+            if (b2 == 0xff && b3 == 0xff) ok = false;
+            else if (b2 == 0xff) { ok = reg_ok(b1) && reg_ok(b3); x = enc(op, F_IR, b1, 0xff, b3); }
+            else if (b3 == 0xff) { ok = reg_ok(b1) && reg_ok(b2); x = enc(op, F_RI, b1, b2, 0xff); }
+            else { ok = reg_ok(b1) && reg_ok(b2) && reg_ok(b3); x = enc(op, F_RR, b1, b2, b3); }
+            if (op_is_choice(op)) {
+                if (b2 == 0xff) ok = false;  // choice ops never have an immediate lhs (ssa_tape.rs:151-176)
+                ++n_choices;
+            }
+        } else {  // OP_MEM
+            if (imm >= mem_count) ok = false;
+            else if (b2 == 0xff && b1 != 0xff) { ok = reg_ok(b1); x = enc(op, F_RI, b1, 0xff, 0xff); }
+            else if (b1 == 0xff && b2 != 0xff) { ok = reg_ok(b2); x = enc(op, F_IR, 0xff, b2, 0xff); }
+            else ok = false;
+        }
+        if (!ok) return fail(FC_ERR_INVALID, "bytecode: malformed clause at word " + std::to_string(i));
+        out.push_back(make_uint2(x, imm));
+    }
+    return FC_OK;
+}
+
+static void to_bytecode(const std::vector<uint2>& cl, std::vector<uint32_t>& words) {
+    words.assign({0xFFFFFFFFu, 0u});
+    for (const uint2& c : cl) {
+        uint32_t dop = c.x & 0xff, op = dop >> 2, form = dop & 3, out = (c.x >> 8) & 0xff, lhs = (c.x >> 16) & 0xff,
+                 rhs = c.x >> 24;
+        uint32_t b1 = 0xff, b2 = 0xff, b3 = 0xff;
+        if (op == OP_OUTPUT) b1 = lhs;
+        else if (op == OP_INPUT) b1 = out;
+        else if (op == OP_COPY) { b1 = out; if (form != F_RI) b2 = lhs; }
+        else if (op_is_unary(op)) { b1 = out; b2 = lhs; }
+        else if (op_is_binary(op)) { b1 = out; if (form != F_IR) b2 = lhs; if (form != F_RI) b3 = rhs; }
+        else { if (form == F_RI) b1 = out; else b2 = lhs; }
+        words.push_back(op | b1 << 8 | b2 << 16 | b3 << 24);
+        words.push_back(c.y);
+    }
+    words.push_back(0xFFFFFFFFu);
+    words.push_back(0xFFFFFFFFu);
+}
+
+extern "C" {
+
+const char* fc_last_error(void) { return g_err.c_str(); }
+uint32_t fc_abi_version(void) { return 1; }
+
+int32_t fc_ctx_create(int32_t device, fc_ctx** out) {
+    if (!out) return fail(FC_ERR_INVALID, "null out");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(FC_ERR_NO_DEVICE, std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                                          "); libfidget_cuda has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(FC_ERR_INVALID, "bad device index");
+    CU(cudaSetDevice(device));
+    fc_ctx* c = new fc_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        delete c;
+        return fail(FC_ERR_NO_DEVICE, "libfidget_cuda is built for sm_100a only; found sm_" +
+                                          std::to_string(prop.major) + std::to_string(prop.minor));
+    }
+    CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    *out = c;
+    return FC_OK;
+}
+
+void fc_ctx_destroy(fc_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->arena.release();
+    for (auto& b : c->jobs) b.release();
+    for (auto& b : c->fills) b.release();
+    c->choice_scratch.release();
+    c->counters.release();
+    c->stats.release();
+    c->image.release();
+    c->heightmap.release();
+    for (auto ev : c->events) cudaEventDestroy(ev);
+    cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int32_t fc_ctx_set_stream(fc_ctx* c, void* s) {
+    if (!c) return fail(FC_ERR_INVALID, "null ctx");
+    c->stream = s ? static_cast<cudaStream_t>(s) : c->own_stream;
+    return FC_OK;
+}
+
+static int32_t check_device_errors(fc_ctx* c) {
+    if (!c->counters.p) return FC_OK;
+    Counters h;
+    CU(cudaMemcpy(&h, c->counters.p, sizeof h, cudaMemcpyDeviceToHost));
+    if (h.error & 1u) return fail(FC_ERR_ARENA, "tape arena exhausted during on-device simplification; raise it with fc_ctx_set_arena_bytes");
+    if (h.error & 2u) return fail(FC_ERR_CUDA, "internal work list overflow");
+    return FC_OK;
+}
+
+int32_t fc_ctx_synchronize(fc_ctx* c) {
+    if (!c) return fail(FC_ERR_INVALID, "null ctx");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return check_device_errors(c);
+}
+
+int32_t fc_ctx_set_arena_bytes(fc_ctx* c, uint64_t bytes) {
+    if (!c || bytes < (1u << 20)) return fail(FC_ERR_INVALID, "arena must be at least 1 MiB");
+    c->arena_bytes = bytes;
+    return FC_OK;
+}
+
+////////////////////////////////////////////////////////////////////////////
+int32_t fc_tape_create(fc_ctx* c, const uint32_t* words, size_t n_words, uint8_t reg_count, uint32_t mem_count,
+                       uint32_t n_vars, uint32_t n_outputs, uint32_t choice_count, fc_tape** out) {
+    if (!c || !out) return fail(FC_ERR_INVALID, "null argument");
+    if (reg_count == 255) return fail(FC_ERR_INVALID, "register 255 is reserved");
+    if (mem_count > 2048 - MEM_BASE) return fail(FC_ERR_UNSUPPORTED, "too many memory slots (max 1792)");
+    std::vector<uint2> cl;
+    uint32_t nch = 0;
+    int32_t rc = transcode(words, n_words, reg_count, mem_count, n_vars, n_outputs, cl, nch);
+    if (rc) return rc;
+    if (nch != choice_count)
+        return fail(FC_ERR_INVALID, "choice_count mismatch: bytecode has " + std::to_string(nch));
+    CU(cudaSetDevice(c->device));
+    fc_tape* t = new fc_tape();
+    t->ctx = c;
+    t->host = cl;
+    t->info.n_ops = uint32_t(cl.size());
+    t->info.ref_len = uint32_t(cl.size());
+    t->info.choice_count = nch;
+    t->info.reg_count = reg_count;
+    t->info.mem_count = mem_count;
+    t->info.n_vars = n_vars;
+    t->info.n_outputs = n_outputs;
+    for (int k = 0; k < 3; ++k) t->ax[k] = uint32_t(k) < n_vars ? k : -1;
+    cudaError_t e = cudaMalloc(&t->dev, std::max<size_t>(cl.size(), 1) * sizeof(uint2));
+    if (e == cudaSuccess && !cl.empty())
+        e = cudaMemcpy(t->dev, cl.data(), cl.size() * sizeof(uint2), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        if (t->dev) cudaFree(t->dev);
+        delete t;
+        return fail(FC_ERR_CUDA, cudaGetErrorString(e));
+    }
+    *out = t;
+    return FC_OK;
+}
+
+int32_t fc_tape_retain(fc_tape* t) {
+    if (!t) return fail(FC_ERR_INVALID, "null tape");
+    t->refs.fetch_add(1);
+    return FC_OK;
+}
+int32_t fc_tape_release(fc_tape* t) {
+    if (!t) return fail(FC_ERR_INVALID, "null tape");
+    if (t->refs.fetch_sub(1) == 1) {
+        cudaSetDevice(t->ctx->device);
+        cudaFree(t->dev);
+        delete t;
+    }
+    return FC_OK;
+}
+int32_t fc_tape_get_info(const fc_tape* t, fc_tape_info* info) {
+    if (!t || !info) return fail(FC_ERR_INVALID, "null argument");
+    *info = t->info;
+    return FC_OK;
+}
+int32_t fc_tape_read(const fc_tape* t, uint32_t* words, size_t cap, size_t* n_words) {
+    if (!t) return fail(FC_ERR_INVALID, "null tape");
+    std::vector<uint32_t> w;
+    to_bytecode(t->host, w);
+    if (n_words) *n_words = w.size();
+    if (words) {
+        if (cap < w.size()) return fail(FC_ERR_INVALID, "buffer too small");
+        memcpy(words, w.data(), w.size() * 4);
+    }
+    return FC_OK;
+}
+
+////////////////////////////////////////////////////////////////////////////
+int32_t fc_eval_create(fc_ctx* c, fc_eval** out) {
+    if (!c || !out) return fail(FC_ERR_INVALID, "null argument");
+    fc_eval* e = new fc_eval();
+    e->ctx = c;
+    *out = e;
+    return FC_OK;
+}
+void fc_eval_destroy(fc_eval* e) {
+    if (!e) return;
+    cudaSetDevice(e->ctx->device);
+    cudaStreamSynchronize(e->ctx->stream);
+    e->in.release(); e->out.release(); e->choices.release(); e->simplify.release(); e->ptrs.release(); e->tmp.release();
+    delete e;
+}
+
+static int32_t tracing_eval(fc_eval* e, const fc_tape* t, const float* vars, uint64_t n, float* out, uint8_t* choices,
+                            uint8_t* simplify, bool interval) {
+    if (!e || !t || (!vars && t->info.n_vars) || !out) return fail(FC_ERR_INVALID, "null argument");
+    fc_ctx* c = e->ctx;
+    CU(cudaSetDevice(c->device));
+    const size_t w = interval ? 2 : 1;
+    const size_t in_bytes = n * t->info.n_vars * w * 4, out_bytes = n * t->info.n_outputs * w * 4;
+    const size_t ch_bytes = n * t->info.choice_count;
+    TracingParams p{};
+    p.tape = t->dev;
+    p.n_ops = t->info.n_ops;
+    p.n_vars = t->info.n_vars;
+    p.n_outputs = t->info.n_outputs;
+    p.n_choices = t->info.choice_count;
+    p.n_slots = MEM_BASE + t->info.mem_count;
+    p.n = n;
+    const bool dv = is_device_ptr(vars), dout = is_device_ptr(out), dch = is_device_ptr(choices),
+               dsi = is_device_ptr(simplify);
+    if (dv || !in_bytes) p.vars = vars;
+    else {
+        CU(e->in.ensure(in_bytes));
+        CU(cudaMemcpyAsync(e->in.p, vars, in_bytes, cudaMemcpyHostToDevice, c->stream));
+        p.vars = e->in.as<float>();
+    }
+    if (dout) p.out = out; else { CU(e->out.ensure(std::max<size_t>(out_bytes, 4))); p.out = e->out.as<float>(); }
+    if (choices && ch_bytes) {
+        if (dch) p.choices = choices; else { CU(e->choices.ensure(ch_bytes)); p.choices = e->choices.as<uint8_t>(); }
+    }
+    if (simplify) {
+        if (dsi) p.simplify = simplify; else { CU(e->simplify.ensure(n)); p.simplify = e->simplify.as<uint8_t>(); }
+    }
+    if (interval) launch_interval_batch(p, c->stream); else launch_point_batch(p, c->stream);
+    CU(cudaGetLastError());
+    if (!dout && out_bytes) CU(cudaMemcpyAsync(out, p.out, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (choices && ch_bytes && !dch) CU(cudaMemcpyAsync(choices, p.choices, ch_bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (simplify && !dsi) CU(cudaMemcpyAsync(simplify, p.simplify, n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return FC_OK;
+}
+
+int32_t fc_interval_eval(fc_eval* e, const fc_tape* t, const float* vars, float* out, uint8_t* choices, uint8_t* simplify) {
+    return tracing_eval(e, t, vars, 1, out, choices, simplify, true);
+}
+int32_t fc_point_eval(fc_eval* e, const fc_tape* t, const float* vars, float* out, uint8_t* choices, uint8_t* simplify) {
+    return tracing_eval(e, t, vars, 1, out, choices, simplify, false);
+}
+int32_t fc_interval_eval_batch(fc_eval* e, const fc_tape* t, const float* vars, uint64_t n, float* out, uint8_t* choices,
+                               uint8_t* simplify) {
+    return tracing_eval(e, t, vars, n, out, choices, simplify, true);
+}
+
+static int32_t bulk_eval(fc_eval* e, const fc_tape* t, const void* const* vars, void* const* outs, uint64_t n,
+                         size_t elem, bool grad) {
+    if (!e || !t || (!vars && t->info.n_vars) || !outs) return fail(FC_ERR_INVALID, "null argument");
+    fc_ctx* c = e->ctx;
+    CU(cudaSetDevice(c->device));
+    const uint32_t nv = t->info.n_vars, no = t->info.n_outputs;
+    std::vector<const void*> dptr(nv + no);
+    // stage host inputs / outputs in the evaluator's buffers
+    size_t in_need = 0, out_need = 0;
+    for (uint32_t i = 0; i < nv; ++i) if (!is_device_ptr(vars[i])) in_need += n * elem;
+    for (uint32_t o = 0; o < no; ++o) if (!is_device_ptr(outs[o])) out_need += n * elem;
+    CU(e->in.ensure(std::max<size_t>(in_need, 16)));
+    CU(e->out.ensure(std::max<size_t>(out_need, 16)));
+    size_t io = 0, oo = 0;
+    std::vector<std::pair<void*, void*>> copy_back;
+    for (uint32_t i = 0; i < nv; ++i) {
+        if (is_device_ptr(vars[i])) dptr[i] = vars[i];
+        else {
+            char* d = e->in.as<char>() + io;
+            if (n) CU(cudaMemcpyAsync(d, vars[i], n * elem, cudaMemcpyHostToDevice, c->stream));
+            dptr[i] = d;
+            io += n * elem;
+        }
+    }
+    for (uint32_t o = 0; o < no; ++o) {
+        if (is_device_ptr(outs[o])) dptr[nv + o] = outs[o];
+        else {
+            char* d = e->out.as<char>() + oo;
+            dptr[nv + o] = d;
+            copy_back.push_back({outs[o], d});
+            oo += n * elem;
+        }
+    }
+    CU(e->ptrs.ensure(std::max<size_t>(dptr.size(), 1) * sizeof(void*)));
+    if (!dptr.empty())
+        CU(cudaMemcpyAsync(e->ptrs.p, dptr.data(), dptr.size() * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
+    BulkParams p{};
+    p.tape = t->dev;
+    p.n_ops = t->info.n_ops;
+    p.n_vars = nv;
+    p.n_outputs = no;
+    p.n_slots = MEM_BASE + t->info.mem_count;
+    p.n = n;
+    p.vars = e->ptrs.as<const void*>();
+    p.outs = reinterpret_cast<void* const*>(e->ptrs.as<void*>() + nv);
+    if (grad) launch_grad_slice(p, c->stream); else launch_float_slice(p, c->stream);
+    CU(cudaGetLastError());
+    for (auto& cb : copy_back)
+        if (n) CU(cudaMemcpyAsync(cb.first, cb.second, n * elem, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return FC_OK;
+}
+
+int32_t fc_float_slice_eval(fc_eval* e, const fc_tape* t, const float* const* vars, float* const* out, uint64_t n) {
+    return bulk_eval(e, t, reinterpret_cast<const void* const*>(vars), reinterpret_cast<void* const*>(out), n, 4, false);
+}
+int32_t fc_grad_slice_eval(fc_eval* e, const fc_tape* t, const fc_grad* const* vars, fc_grad* const* out, uint64_t n) {
+    return bulk_eval(e, t, reinterpret_cast<const void* const*>(vars), reinterpret_cast<void* const*>(out), n, 16, true);
+}
+
+int32_t fc_simplify(fc_eval* e, const fc_tape* parent, const uint8_t* choices, size_t n_choices, fc_tape** child) {
+    if (!e || !parent || !child || (!choices && n_choices)) return fail(FC_ERR_INVALID, "null argument");
+    if (n_choices != parent->info.choice_count)
+        return fail(FC_ERR_INVALID, "choice slice length (" + std::to_string(n_choices) + ") does not match choice count (" +
+                                        std::to_string(parent->info.choice_count) + ")");
+    if (parent->info.mem_count) return fail(FC_ERR_UNSUPPORTED, "fc_simplify: parent tape uses memory slots");
+    for (size_t i = 0; i < n_choices; ++i)
+        if (choices[i] < 1 || choices[i] > 3) return fail(FC_ERR_INVALID, "trace contains Choice::Unknown");
+    fc_ctx* c = e->ctx;
+    CU(cudaSetDevice(c->device));
+    const uint32_t n = parent->info.n_ops;
+    CU(e->tmp.ensure(std::max<size_t>(n, 1) * sizeof(uint2) + 16));
+    CU(e->choices.ensure(std::max<size_t>(n_choices, 1)));
+    if (n_choices) CU(cudaMemcpyAsync(e->choices.p, choices, n_choices, cudaMemcpyHostToDevice, c->stream));
+    SimplifyParams p{};
+    p.parent = parent->dev;
+    p.n_ops = n;
+    p.parent_ref_len = parent->info.ref_len;
+    p.choices = e->choices.as<uint8_t>();
+    p.n_choices = uint32_t(n_choices);
+    p.out = e->tmp.as<uint2>();
+    p.result = reinterpret_cast<uint32_t*>(e->tmp.as<char>() + size_t(n) * sizeof(uint2));
+    launch_simplify_single(p, c->stream);
+    CU(cudaGetLastError());
+    uint32_t res[3];
+    CU(cudaMemcpyAsync(res, p.result, sizeof res, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    fc_tape* t = new fc_tape();
+    t->ctx = c;
+    t->info = parent->info;
+    memcpy(t->ax, parent->ax, sizeof t->ax);
+    t->info.n_ops = res[0];
+    t->info.ref_len = res[1];
+    t->info.choice_count = res[2];
+    t->host.resize(res[0]);
+    cudaError_t err = cudaMalloc(&t->dev, std::max<size_t>(res[0], 1) * sizeof(uint2));
+    if (err == cudaSuccess && res[0]) {
+        err = cudaMemcpy(t->dev, p.out + (n - res[0]), res[0] * sizeof(uint2), cudaMemcpyDeviceToDevice);
+        if (err == cudaSuccess) err = cudaMemcpy(t->host.data(), t->dev, res[0] * sizeof(uint2), cudaMemcpyDeviceToHost);
+    }
+    if (err != cudaSuccess) {
+        if (t->dev) cudaFree(t->dev);
+        delete t;
+        return fail(FC_ERR_CUDA, cudaGetErrorString(err));
+    }
+    *child = t;
+    return FC_OK;
+}
+
+////////////////////////////////////////////////////////////////////////////
+// Renderers
+
+// TileSizesRef::new (fidget-raster/src/lib.rs:59-66)
+static int32_t pick_tile_sizes(const uint32_t* ts_in, uint32_t n_in, const uint32_t* dflt, uint32_t n_dflt,
+                               uint32_t max_size, std::vector<uint32_t>& ts) {
+    std::vector<uint32_t> all(n_in ? ts_in : dflt, n_in ? ts_in + n_in : dflt + n_dflt);
+    if (all.empty() || all.size() > FC_MAX_TILE_LEVELS) return fail(FC_ERR_INVALID, "bad tile size count");
+    for (size_t i = 0; i < all.size(); ++i) {
+        if (all[i] == 0) return fail(FC_ERR_INVALID, "tile size 0");
+        if (i && (all[i - 1] <= all[i] || all[i - 1] % all[i]))
+            return fail(FC_ERR_INVALID, "tile sizes must decrease and divide each other");
+    }
+    size_t pos = all.size();
+    for (size_t i = 0; i < all.size(); ++i) if (all[i] < max_size) { pos = i; break; }
+    size_t start = pos ? pos - 1 : 0;
+    ts.assign(all.begin() + start, all.end());
+    return FC_OK;
+}
+
+struct AxisMap { int x, y, z; };
+
+// Binds tape input slots to the X, Y, Z axes (ShapeTape::vars(),
+// shape/mod.rs:355-376); -1 = axis unused.
+int32_t fc_tape_set_axes(fc_tape* t, int32_t x, int32_t y, int32_t z) {
+    if (!t) return fail(FC_ERR_INVALID, "null tape");
+    int nv = int(t->info.n_vars);
+    if (x >= nv || y >= nv || z >= nv) return fail(FC_ERR_INVALID, "axis slot out of range");
+    t->ax[0] = x; t->ax[1] = y; t->ax[2] = z;
+    return FC_OK;
+}
+
+static AxisMap axes_of(const fc_tape* t) { return AxisMap{t->ax[0], t->ax[1], t->ax[2]}; }
+
+static cudaEvent_t get_event(fc_ctx* c, size_t i) {
+    while (c->events.size() <= i) {
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        c->events.push_back(ev);
+    }
+    return c->events[i];
+}
+
+int32_t fc_render2d(fc_ctx* c, const fc_tape* tape, const fc_render2d_cfg* cfg, float* out, fc_render_stats* stats) {
+    if (!c || !tape || !cfg || !out) return fail(FC_ERR_INVALID, "null argument");
+    if (cfg->width == 0 || cfg->height == 0) return fail(FC_ERR_INVALID, "empty image");
+    if (tape->info.mem_count) return fail(FC_ERR_UNSUPPORTED, "renderers need a tape without memory spills (<= 254 registers)");
+    if (tape->info.n_outputs != 1) return fail(FC_ERR_INVALID, "ShapeTape has multiple outputs");
+    std::lock_guard<std::mutex> guard(c->mu);
+    CU(cudaSetDevice(c->device));
+    static const uint32_t DFLT[3] = {128, 32, 8};
+    std::vector<uint32_t> ts;
+    int32_t rc = pick_tile_sizes(cfg->tile_sizes, cfg->n_tile_sizes, DFLT, 3, std::max(cfg->width, cfg->height), ts);
+    if (rc) return rc;
+    const int L = int(ts.size());
+    const uint32_t T0 = ts[0];
+    const uint32_t roots_x = (cfg->width + T0 - 1) / T0;
+    uint32_t roots_y_all = (cfg->height + T0 - 1) / T0;
+    uint32_t row0 = cfg->root_row_begin, row1 = cfg->root_row_end ? cfg->root_row_end : roots_y_all;
+    if (row0 > row1 || row1 > roots_y_all) return fail(FC_ERR_INVALID, "bad root row band");
+    const uint32_t roots_y = row1 - row0;
+    const uint64_t n_roots = uint64_t(roots_x) * roots_y;
+    const bool timing = (cfg->flags & FC_FLAG_TIMING) != 0;
+    const bool async = (cfg->flags & FC_FLAG_ASYNC) != 0;
+    const bool want_stats = stats != nullptr;
+    cudaStream_t s = c->stream;
+
+    // ---- scratch ----
+    const int bps = env_int("FIDGET_B200_BLOCKS_PER_SM", 6);
+    const int grid_blocks = c->sm_count * bps;
+    const uint32_t choice_words = (tape->info.choice_count + 15) / 16 + 1;
+    CU(c->choice_scratch.ensure(size_t(grid_blocks) * WARPS_PER_BLOCK * choice_words * 32 * 4));
+    CU(c->arena.ensure(c->arena_bytes));
+    CU(c->counters.ensure(sizeof(Counters)));
+    CU(c->stats.ensure(sizeof(Stats)));
+    std::vector<uint64_t> level_tiles(L + 1);
+    for (int l = 1; l <= L; ++l) {
+        // jobs queued for level l are tiles of size ts[l-1]
+        uint64_t per_root = uint64_t(T0 / ts[l - 1]) * (T0 / ts[l - 1]);
+        level_tiles[l] = n_roots * per_root;
+        if (level_tiles[l] > 0xfffffff0ull) return fail(FC_ERR_UNSUPPORTED, "image too large for 32-bit tile lists");
+        CU(c->jobs[l].ensure(level_tiles[l] * sizeof(TileJob)));
+        CU(c->fills[l - 1].ensure(level_tiles[l] * sizeof(FillRec)));
+    }
+    const bool out_dev = is_device_ptr(out);
+    float* dimg = out;
+    const size_t img_bytes = size_t(cfg->width) * cfg->height * 4;
+    if (!out_dev) {
+        CU(c->image.ensure(img_bytes));
+        dimg = c->image.as<float>();
+    }
+    CU(cudaMemsetAsync(c->counters.p, 0, sizeof(Counters), s));
+    if (want_stats) CU(cudaMemsetAsync(c->stats.p, 0, sizeof(Stats), s));
+    if (roots_y != roots_y_all || cfg->width % T0 || cfg->height % T0) {
+        // pixels outside the rendered band keep RawDistancePixel::default() = 0.0
+        if (roots_y != roots_y_all) CU(cudaMemsetAsync(dimg, 0, img_bytes, s));
+    }
+
+    AxisMap ax = axes_of(tape);
+    size_t ev = 0;
+    if (timing) CU(cudaEventRecord(get_event(c, ev++), s));
+    uint32_t launches = 0;
+    for (int l = 0; l < L; ++l) {
+        LevelParams p{};
+        p.level = l;
+        p.tile = ts[l];
+        p.n_axis = l ? ts[l - 1] / ts[l] : 0;
+        p.is_last = (l == L - 1);
+        p.pixel_perfect = cfg->pixel_perfect;
+        p.root_mode = (l == 0);
+        p.roots_x = roots_x; p.roots_y = roots_y; p.roots_z = 1;
+        p.root_x0 = 0; p.root_y0 = row0 * T0; p.root_z0 = 0;
+        p.root_tape.ptr = tape->dev;
+        p.root_tape.n_ops = tape->info.n_ops;
+        p.root_tape.ref_len = tape->info.ref_len;
+        p.root_tape.n_choices = tape->info.choice_count;
+        p.width = cfg->width; p.height = cfg->height; p.depth = 1;
+        p.z2d = cfg->z;
+        memcpy(p.mat.m, cfg->mat, sizeof p.mat.m);
+        p.jobs_in = l ? c->jobs[l].as<TileJob>() : nullptr;
+        p.jobs_out = c->jobs[l + 1].as<TileJob>();
+        p.cap_out = uint32_t(level_tiles[l + 1]);
+        p.fills = c->fills[l].as<FillRec>();
+        p.cap_fills = uint32_t(level_tiles[l + 1]);
+        p.arena = c->arena.as<uint2>();
+        p.arena_cap = c->arena.cap / sizeof(uint2);
+        p.choice_scratch = c->choice_scratch.as<uint32_t>();
+        p.choice_words = choice_words;
+        p.ctr = c->counters.as<Counters>();
+        p.stats = want_stats ? c->stats.as<Stats>() : nullptr;
+        p.var_x = ax.x; p.var_y = ax.y; p.var_z = ax.z;
+        int blocks = grid_blocks;
+        if (l == 0) {
+            uint64_t warps = (n_roots + 31) / 32;
+            blocks = int(std::min<uint64_t>((warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, uint64_t(grid_blocks)));
+        }
+        launch_interval_level_2d(p, std::max(blocks, 1), s);
+        ++launches;
+        if (timing) CU(cudaEventRecord(get_event(c, ev++), s));
+    }
+    for (int l = 0; l < L; ++l) {
+        FillParams f{};
+        f.tile = ts[l];
+        f.width = cfg->width; f.height = cfg->height;
+        f.fills = c->fills[l].as<FillRec>();
+        f.n_fills = &c->counters.as<Counters>()->n_fills[l];
+        f.out = dimg;
+        launch_fill_2d(f, c->sm_count * 4, s);
+        ++launches;
+    }
+    if (timing) CU(cudaEventRecord(get_event(c, ev++), s));
+    {
+        PixelParams q{};
+        q.tile = ts[L - 1];
+        q.width = cfg->width; q.height = cfg->height;
+        q.z2d = cfg->z;
+        memcpy(q.mat.m, cfg->mat, sizeof q.mat.m);
+        q.jobs = c->jobs[L].as<TileJob>();
+        q.out = dimg;
+        q.ctr = c->counters.as<Counters>();
+        q.list = L;
+        q.cursor = L;
+        q.stats = want_stats ? c->stats.as<Stats>() : nullptr;
+        q.var_x = ax.x; q.var_y = ax.y; q.var_z = ax.z;
+        launch_pixels_2d(q, c->sm_count * env_int("FIDGET_B200_PIXEL_BLOCKS_PER_SM", 8), s);
+        ++launches;
+    }
+    if (timing) CU(cudaEventRecord(get_event(c, ev++), s));
+    CU(cudaGetLastError());
+    if (!out_dev) CU(cudaMemcpyAsync(out, dimg, img_bytes, cudaMemcpyDeviceToHost, s));
+    if (async && out_dev && !want_stats) return FC_OK;
+    CU(cudaStreamSynchronize(s));
+    rc = check_device_errors(c);
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        Stats h;
+        Counters hc;
+        CU(cudaMemcpy(&h, c->stats.p, sizeof h, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(&hc, c->counters.p, sizeof hc, cudaMemcpyDeviceToHost));
+        for (int l = 0; l < MAX_LEVELS; ++l) {
+            stats->evaluated[l] = h.evaluated[l];
+            stats->filled_inside[l] = h.filled_inside[l];
+            stats->filled_outside[l] = h.filled_outside[l];
+            stats->ambiguous[l] = h.ambiguous[l];
+            stats->simplified[l] = h.simplified[l];
+        }
+        stats->pixels = h.pixels;
+        stats->arena_bytes_used = hc.arena_top * sizeof(uint2);
+        stats->kernel_launches = launches;
+        if (timing) {
+            float ms = 0;
+            for (int l = 0; l < L; ++l) {
+                cudaEventElapsedTime(&ms, c->events[l], c->events[l + 1]);
+                stats->stage_ms[l] = ms;
+            }
+            cudaEventElapsedTime(&ms, c->events[L], c->events[L + 1]);
+            stats->stage_ms[8] = ms;
+            cudaEventElapsedTime(&ms, c->events[L + 1], c->events[L + 2]);
+            stats->stage_ms[9] = ms;
+            cudaEventElapsedTime(&ms, c->events[0], c->events[L + 2]);
+            stats->stage_ms[15] = ms;
+        }
+    }
+    return rc;
+}
+
+int32_t fc_render3d(fc_ctx*, const fc_tape*, const fc_render3d_cfg*, fc_geometry_pixel*, fc_render_stats*) {
+    return fail(FC_ERR_UNSUPPORTED, "fc_render3d: not built yet");
+}
+int32_t fc_merge_slabs(fc_ctx*, const fc_geometry_pixel* const*, uint32_t, uint32_t, uint32_t, uint32_t,
+                       fc_geometry_pixel*) {
+    return fail(FC_ERR_UNSUPPORTED, "fc_merge_slabs: not built yet");
+}
+
+}  // extern "C"

@@ -1,0 +1,678 @@
+// sm_100a kernels for the tape-evaluation hot path.
+//
+//  k_interval_level  -- K1: one warp per parent tile, one lane per child tile;
+//                       walks the (warp-uniform) parent tape, classifies each
+//                       child (fill inside / fill outside / ambiguous), then
+//                       runs the reverse liveness pass that compacts a child
+//                       tape into the arena (VmData::simplify semantics,
+//                       fidget-core/src/vm/data.rs:123-318) and queues the
+//                       ambiguous children for the next level
+//                       (pixel.rs:316-398 / voxel.rs:275-357).
+//  k_pixels_2d       -- K2: one warp per leaf tile, two pixels per lane
+//                       (pixel.rs:400-440 + VmFloatSliceEval, vm/mod.rs:800).
+//  k_fill_2d         -- paints interval-proven tiles (pixel.rs:345-369).
+//  k_float_slice / k_grad_slice / k_interval_batch / k_point_batch /
+//  k_simplify_single -- the trait-level evaluators behind fc_*_eval.
+//
+// All interpreters keep the tape's VM registers in per-thread local memory
+// (L1-resident, lane-interleaved, so a warp's access to one register is one
+// 128/256-byte line) and read tape clauses with warp-uniform 8-byte loads.
+#include <cstdio>
+
+#include "kernels.cuh"
+
+namespace fdev {
+
+#define FULL 0xffffffffu
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+struct Dec {
+    uint32_t op, form, out, lhs, rhs;
+    __device__ __forceinline__ explicit Dec(uint32_t x) {
+        uint32_t dop = x & 0xffu;
+        op = dop >> 2;
+        form = dop & 3u;
+        out = (x >> 8) & 0xffu;
+        lhs = (x >> 16) & 0xffu;
+        rhs = x >> 24;
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Interval interpreter.  `Input` maps a variable index to an interval,
+// `Sink` receives one choice per choice clause in evaluation order, `Out`
+// receives (output index, value).
+template <class Input, class Sink, class Out>
+__device__ __forceinline__ void run_interval(const uint2* __restrict__ tape, uint32_t n_ops, itv* slots,
+                                             Input input, Sink& sink, Out out_fn) {
+    if (n_ops == 0) return;
+    uint2 w = __ldg(tape);
+    for (uint32_t i = 0; i < n_ops; ++i) {
+        uint2 nxt = __ldg(tape + (i + 1 < n_ops ? i + 1 : i));
+        Dec d(w.x);
+        float imm = __uint_as_float(w.y);
+        itv sl = slots[d.lhs], sr = slots[d.rhs];
+        itv a = d.form == F_IR ? iv1(imm) : sl;
+        itv b = d.form == F_RI ? iv1(imm) : sr;
+        itv r;
+        if (d.op >= OP_MIN) {
+            if (d.op == OP_MEM) {
+                if (d.form == F_RI) slots[d.out] = slots[MEM_BASE + w.y];
+                else slots[MEM_BASE + w.y] = sl;
+                w = nxt;
+                continue;
+            }
+            uint32_t c;
+            r = iv_choice_op(d.op, a, b, c);
+            sink.push(c);
+        } else if (d.op >= OP_ADD) {
+            if (d.op == OP_MUL && d.form == F_RI) r = iv_mul_f(sl, imm);
+            else r = iv_binary(d.op, a, b);
+        } else if (d.op >= OP_NEG) {
+            r = iv_unary(d.op, sl);
+        } else if (d.op == OP_COPY) {
+            r = d.form == F_RI ? iv1(imm) : sl;
+        } else if (d.op == OP_INPUT) {
+            r = input(w.y);
+        } else {  // OP_OUTPUT
+            out_fn(w.y, sl);
+            w = nxt;
+            continue;
+        }
+        slots[d.out] = r;
+        w = nxt;
+    }
+}
+
+// Two-points-per-lane f32 interpreter
+__device__ __forceinline__ float2 f32x2_unary(uint32_t op, float2 a) {
+    switch (op) {
+        case OP_NEG: return make_float2(-a.x, -a.y);
+        case OP_ABS: return make_float2(fabsf(a.x), fabsf(a.y));
+        case OP_SQRT: return make_float2(sqrtf(a.x), sqrtf(a.y));
+        case OP_SQUARE: return make_float2(a.x * a.x, a.y * a.y);
+        default: return make_float2(f32_unary(op, a.x), f32_unary(op, a.y));
+    }
+}
+__device__ __forceinline__ float2 f32x2_binary(uint32_t op, float2 a, float2 b) {
+    switch (op) {
+        case OP_ADD: return make_float2(a.x + b.x, a.y + b.y);
+        case OP_SUB: return make_float2(a.x - b.x, a.y - b.y);
+        case OP_MUL: return make_float2(a.x * b.x, a.y * b.y);
+        case OP_MIN: return make_float2(f_min(a.x, b.x), f_min(a.y, b.y));
+        case OP_MAX: return make_float2(f_max(a.x, b.x), f_max(a.y, b.y));
+        default: return make_float2(f32_binary(op, a.x, b.x), f32_binary(op, a.y, b.y));
+    }
+}
+
+template <class Input>
+__device__ __forceinline__ float2 run_f32x2(const uint2* __restrict__ tape, uint32_t n_ops, float2* slots,
+                                            Input input) {
+    float2 result = make_float2(nanf_(), nanf_());
+    if (n_ops == 0) return result;
+    uint2 w = __ldg(tape);
+    for (uint32_t i = 0; i < n_ops; ++i) {
+        uint2 nxt = __ldg(tape + (i + 1 < n_ops ? i + 1 : i));
+        Dec d(w.x);
+        float imm = __uint_as_float(w.y);
+        float2 sl = slots[d.lhs], sr = slots[d.rhs];
+        float2 a = d.form == F_IR ? make_float2(imm, imm) : sl;
+        float2 b = d.form == F_RI ? make_float2(imm, imm) : sr;
+        float2 r;
+        if (d.op >= OP_ADD) {
+            if (d.op == OP_MEM) {
+                if (d.form == F_RI) slots[d.out] = slots[MEM_BASE + w.y];
+                else slots[MEM_BASE + w.y] = sl;
+                w = nxt;
+                continue;
+            }
+            r = f32x2_binary(d.op, a, b);
+        } else if (d.op >= OP_NEG) {
+            r = f32x2_unary(d.op, sl);
+        } else if (d.op == OP_COPY) {
+            r = d.form == F_RI ? make_float2(imm, imm) : sl;
+        } else if (d.op == OP_INPUT) {
+            r = input(w.y);
+        } else {
+            if (w.y == 0) result = sl;
+            w = nxt;
+            continue;
+        }
+        slots[d.out] = r;
+        w = nxt;
+    }
+    return result;
+}
+
+// ---------------------------------------------------------------------------
+// Choice storage for the level kernel: 2 bits per choice, 16 per word, words
+// interleaved across the 32 lanes of the warp.
+struct ChoicePacker {
+    uint32_t* base;  // already offset by lane; stride 32
+    uint32_t acc = 0, ci = 0;
+    bool any_nonboth = false;
+    __device__ __forceinline__ void push(uint32_t c) {
+        acc |= c << ((ci & 15u) * 2u);
+        any_nonboth |= (c != 3u);
+        ++ci;
+        if ((ci & 15u) == 0u) {
+            base[((ci >> 4) - 1u) * 32u] = acc;
+            acc = 0;
+        }
+    }
+    __device__ __forceinline__ void finish() {
+        if (ci & 15u) base[(ci >> 4) * 32u] = acc;
+    }
+};
+struct ChoiceUnpacker {
+    const uint32_t* base;
+    uint32_t ci;       // choices remaining
+    uint32_t cached_word = 0xffffffffu, cur = 0;
+    __device__ __forceinline__ uint32_t pop() {
+        --ci;
+        uint32_t wi = ci >> 4;
+        if (wi != cached_word) {
+            cur = base[wi * 32u];
+            cached_word = wi;
+        }
+        return (cur >> ((ci & 15u) * 2u)) & 3u;
+    }
+};
+struct ByteChoiceSource {
+    const uint8_t* base;
+    uint32_t ci;
+    __device__ __forceinline__ uint32_t pop() { return base[--ci] & 3u; }
+};
+
+// Reverse liveness pass + compaction (VmData::simplify on a register tape that
+// keeps the parent's register assignment).  Writes the child tape backwards,
+// ending at `wend`.  `live` is this warp's [8][32] bitset in shared memory.
+template <class ChoiceSrc>
+__device__ __forceinline__ void simplify_lane(const uint2* __restrict__ tape, uint32_t n_ops, bool active,
+                                              uint32_t (*live)[32], int lane, ChoiceSrc& cs, uint2* wend,
+                                              uint32_t& n_dev, uint32_t& ref_len, uint32_t& n_choices) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) live[k][lane] = 0;
+    auto test = [&](uint32_t r) { return (live[r >> 5][lane] >> (r & 31u)) & 1u; };
+    auto set = [&](uint32_t r) { live[r >> 5][lane] |= 1u << (r & 31u); };
+    auto clear = [&](uint32_t r) { live[r >> 5][lane] &= ~(1u << (r & 31u)); };
+    uint2* wp = wend;
+    uint32_t ref = 0, nch = 0;
+    for (int i = int(n_ops) - 1; i >= 0; --i) {
+        uint2 w = __ldg(tape + i);
+        Dec d(w.x);
+        uint32_t c = 3u;
+        bool is_choice = op_is_choice(d.op);
+        if (is_choice) c = cs.pop();
+        if (!active) continue;
+        if (d.op == OP_OUTPUT) {
+            set(d.lhs);
+            *--wp = w;
+            ++ref;
+            continue;
+        }
+        if (!test(d.out)) continue;
+        clear(d.out);
+        if (is_choice && c != 3u) {
+            if (c == 2u && d.form == F_RI) {
+                *--wp = make_uint2(enc(OP_COPY, F_RI, d.out, 0xff, 0xff), w.y);
+                ++ref;
+            } else {
+                // F_RI keeps its register in lhs; F_RR left = lhs, right = rhs
+                uint32_t src = (c == 1u) ? d.lhs : d.rhs;
+                if (src == d.out) {
+                    set(d.out);
+                } else {
+                    uint32_t was = test(src);
+                    set(src);
+                    *--wp = make_uint2(enc(OP_COPY, was ? F_RR : F_ALIAS, d.out, src, 0xff), 0xFF000000u);
+                    ref += was;
+                }
+            }
+            continue;
+        }
+        if (d.op == OP_COPY && d.form != F_RI) {
+            uint32_t src = d.lhs;
+            if (src == d.out) { set(d.out); continue; }
+            uint32_t was = test(src);
+            set(src);
+            uint32_t nf = (d.form == F_ALIAS || !was) ? F_ALIAS : F_RR;
+            *--wp = make_uint2(enc(OP_COPY, nf, d.out, src, 0xff), w.y);
+            ref += (nf == F_RR);
+            continue;
+        }
+        *--wp = w;
+        ++ref;
+        if (is_choice) ++nch;
+        if (d.op == OP_INPUT || d.op == OP_COPY) continue;
+        if (d.op < OP_ADD) set(d.lhs);
+        else {
+            if (d.form != F_IR) set(d.lhs);
+            if (d.form != F_RI) set(d.rhs);
+        }
+    }
+    n_dev = uint32_t(wend - wp);
+    ref_len = ref;
+    n_choices = nch;
+}
+
+// ---------------------------------------------------------------------------
+// K1: interval level kernel (2D)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_interval_level_2d(const __grid_constant__ LevelParams p) {
+    __shared__ uint32_t live_s[WARPS_PER_BLOCK][8][32];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const uint32_t gw = blockIdx.x * WARPS_PER_BLOCK + wib;
+    uint32_t* cs = p.choice_scratch + size_t(gw) * p.choice_words * 32u + lane;
+    itv slots[REG_SLOTS];
+
+    const uint32_t n_roots = p.roots_x * p.roots_y;
+    const uint32_t n_jobs = p.root_mode ? (n_roots + 31u) / 32u : p.ctr->n_jobs[p.level];
+    const uint32_t T = p.tile;
+
+    for (;;) {
+        uint32_t j = 0;
+        if (lane == 0) j = atomicAdd(&p.ctr->cursor[p.level], 1u);
+        j = __shfl_sync(FULL, j, 0);
+        if (j >= n_jobs) break;
+
+        TapeRef tr;
+        uint32_t px = 0, py = 0, nchild;
+        if (p.root_mode) {
+            tr = p.root_tape;
+            nchild = min(32u, n_roots - j * 32u);
+        } else {
+            const TileJob* job = p.jobs_in + j;
+            px = job->x;
+            py = job->y;
+            tr = job->tape;
+            nchild = p.n_axis * p.n_axis;
+        }
+        const uint2* tape = tr.ptr;
+
+        for (uint32_t chunk = 0; chunk * 32u < nchild; ++chunk) {
+            const uint32_t c = chunk * 32u + lane;
+            const bool valid = c < nchild;
+            uint32_t cx, cy;
+            if (p.root_mode) {
+                uint32_t idx = j * 32u + (valid ? c : 0u);
+                cx = p.root_x0 + (idx % p.roots_x) * T;
+                cy = p.root_y0 + (idx / p.roots_x) * T;
+            } else {
+                uint32_t cc = valid ? c : 0u;
+                cx = px + (cc % p.n_axis) * T;
+                cy = py + (cc / p.n_axis) * T;
+            }
+            // Region in screen coordinates -> model space (pixel.rs:325-342)
+            itv X = iv(float(cx), float(cx) + float(T));
+            itv Y = iv(float(cy), float(cy) + float(T));
+            itv Z = iv(p.z2d, p.z2d);
+            itv vx, vy, vz;
+            xform_iv(p.mat, X, Y, Z, vx, vy, vz);
+
+            ChoicePacker pk;
+            pk.base = cs;
+            itv r = iv_nan();
+            const int ix = p.var_x, iy = p.var_y;
+            run_interval(
+                tape, tr.n_ops, slots,
+                [&](uint32_t i) { return int(i) == ix ? vx : (int(i) == iy ? vy : vz); }, pk,
+                [&](uint32_t oi, itv v) { if (oi == 0) r = v; });
+            pk.finish();
+
+            const bool fill_in = valid && !p.pixel_perfect && r.y < 0.0f;
+            const bool fill_out = valid && !p.pixel_perfect && !fill_in && r.x > 0.0f;
+            const bool amb = valid && !fill_in && !fill_out;
+
+            // fills
+            {
+                uint32_t m = __ballot_sync(FULL, fill_in || fill_out);
+                if (m) {
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(&p.ctr->n_fills[p.level], uint32_t(__popc(m)));
+                    base = __shfl_sync(FULL, base, 0);
+                    if (fill_in || fill_out) {
+                        uint32_t slot = base + __popc(m & lanemask_lt());
+                        if (slot < p.cap_fills) {
+                            FillRec fr;
+                            fr.x = cx;
+                            fr.y = cy;
+                            fr.value = 0x7FC00000u | (uint32_t(p.level & 0xff) << 1) | (fill_in ? 1u : 0u) | (0xF6u << 9);
+                            p.fills[slot] = fr;
+                        } else {
+                            atomicOr(&p.ctr->error, 2u);
+                        }
+                    }
+                }
+                if (p.stats) {
+                    uint32_t mv = __ballot_sync(FULL, valid), mi = __ballot_sync(FULL, fill_in),
+                             mo = __ballot_sync(FULL, fill_out), ma = __ballot_sync(FULL, amb);
+                    if (lane == 0) {
+                        atomicAdd(&p.stats->evaluated[p.level], (unsigned long long)__popc(mv));
+                        if (mi) atomicAdd(&p.stats->filled_inside[p.level], (unsigned long long)__popc(mi));
+                        if (mo) atomicAdd(&p.stats->filled_outside[p.level], (unsigned long long)__popc(mo));
+                        if (ma) atomicAdd(&p.stats->ambiguous[p.level], (unsigned long long)__popc(ma));
+                    }
+                }
+            }
+
+            // simplification (render/mod.rs:96-152: keep the child only if it is shorter)
+            TapeRef child = tr;
+            const bool need = amb && pk.any_nonboth;
+            const uint32_t mneed = __ballot_sync(FULL, need);
+            if (mneed) {
+                const uint32_t total = __popc(mneed);
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(&p.ctr->arena_top, (unsigned long long)total * tr.n_ops);
+                base = __shfl_sync(FULL, base, 0);
+                if (base + (unsigned long long)total * tr.n_ops > p.arena_cap) {
+                    if (lane == 0) atomicOr(&p.ctr->error, 1u);
+                } else {
+                    const uint32_t rank = __popc(mneed & lanemask_lt());
+                    unsigned long long end = base + (unsigned long long)(rank + 1u) * tr.n_ops;
+                    ChoiceUnpacker cu;
+                    cu.base = cs;
+                    cu.ci = tr.n_choices;
+                    uint32_t n_dev, ref_len, nch;
+                    simplify_lane(tape, tr.n_ops, need, live_s[wib], lane, cu, p.arena + end, n_dev, ref_len, nch);
+                    bool keep = need && ref_len < tr.ref_len;
+                    if (keep) {
+                        child.ptr = p.arena + (end - n_dev);
+                        child.n_ops = n_dev;
+                        child.ref_len = ref_len;
+                        child.n_choices = nch;
+                    }
+                    if (p.stats) {
+                        uint32_t mk = __ballot_sync(FULL, keep);
+                        if (lane == 0 && mk) atomicAdd(&p.stats->simplified[p.level], (unsigned long long)__popc(mk));
+                    }
+                }
+            }
+
+            // queue ambiguous children for the next level
+            const uint32_t mamb = __ballot_sync(FULL, amb);
+            if (mamb) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&p.ctr->n_jobs[p.level + 1], uint32_t(__popc(mamb)));
+                base = __shfl_sync(FULL, base, 0);
+                if (amb) {
+                    uint32_t slot = base + __popc(mamb & lanemask_lt());
+                    if (slot < p.cap_out) {
+                        TileJob o;
+                        o.x = cx;
+                        o.y = cy;
+                        o.z = 0;
+                        o.pad = 0;
+                        o.tape = child;
+                        p.jobs_out[slot] = o;
+                    } else {
+                        atomicOr(&p.ctr->error, 2u);
+                    }
+                }
+            }
+        }
+    }
+}
+
+void launch_interval_level_2d(const LevelParams& p, int blocks, cudaStream_t s) {
+    k_interval_level_2d<<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(p);
+}
+
+// ---------------------------------------------------------------------------
+// K2: leaf pixels (2D)
+__global__ void __launch_bounds__(128) k_pixels_2d(const __grid_constant__ PixelParams p) {
+    const int lane = threadIdx.x & 31;
+    float2 slots[REG_SLOTS];
+    const uint32_t n_jobs = min(p.ctr->n_jobs[p.list], 0xffffffffu);
+    const uint32_t T = p.tile, npix = T * T;
+    unsigned long long shaded = 0;
+    for (;;) {
+        uint32_t j = 0;
+        if (lane == 0) j = atomicAdd(&p.ctr->cursor[p.cursor], 1u);
+        j = __shfl_sync(FULL, j, 0);
+        if (j >= n_jobs) break;
+        const TileJob* job = p.jobs + j;
+        const uint32_t cx = job->x, cy = job->y;
+        const TapeRef tr = job->tape;
+        const uint2* tape = tr.ptr;
+        for (uint32_t base = 0; base < npix; base += 64u) {
+            uint32_t p0 = base + lane, p1 = p0 + 32u;
+            bool v0 = p0 < npix, v1 = p1 < npix;
+            uint32_t i0 = (v0 ? p0 : 0u) % T, j0 = (v0 ? p0 : 0u) / T;
+            uint32_t i1 = (v1 ? p1 : 0u) % T, j1 = (v1 ? p1 : 0u) / T;
+            float x0, y0, z0, x1, y1, z1;
+            xform_f32(p.mat, float(cx + i0), float(cy + j0), p.z2d, x0, y0, z0);
+            xform_f32(p.mat, float(cx + i1), float(cy + j1), p.z2d, x1, y1, z1);
+            const float2 X = make_float2(x0, x1), Y = make_float2(y0, y1), Z = make_float2(z0, z1);
+            const int ix = p.var_x, iy = p.var_y;
+            float2 r = run_f32x2(tape, tr.n_ops, slots,
+                                 [&](uint32_t i) { return int(i) == ix ? X : (int(i) == iy ? Y : Z); });
+            // RawDistancePixel::from(f32): canonical NaN (pixel.rs:234-240)
+            if (r.x != r.x) r.x = nanf_();
+            if (r.y != r.y) r.y = nanf_();
+            uint32_t gx0 = cx + i0, gy0 = cy + j0, gx1 = cx + i1, gy1 = cy + j1;
+            if (v0 && gx0 < p.width && gy0 < p.height) p.out[size_t(gy0) * p.width + gx0] = r.x;
+            if (v1 && gx1 < p.width && gy1 < p.height) p.out[size_t(gy1) * p.width + gx1] = r.y;
+            shaded += (v0 ? 1 : 0) + (v1 ? 1 : 0);
+        }
+    }
+    if (p.stats) {
+        for (int o = 16; o > 0; o >>= 1) shaded += __shfl_xor_sync(FULL, shaded, o);
+        if (lane == 0 && shaded) atomicAdd(&p.stats->pixels, shaded);
+    }
+}
+
+void launch_pixels_2d(const PixelParams& p, int blocks, cudaStream_t s) { k_pixels_2d<<<blocks, 128, 0, s>>>(p); }
+
+// ---------------------------------------------------------------------------
+// Fill painter: one warp per (record, 1024-pixel unit)
+__global__ void __launch_bounds__(256) k_fill_2d(const __grid_constant__ FillParams p) {
+    const uint32_t n = *p.n_fills;
+    const uint32_t T = p.tile;
+    const uint32_t tile_px = T * T;
+    const uint32_t unit_px = min(tile_px, 1024u);
+    const uint32_t units = tile_px / unit_px;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    const bool vec_ok = (p.width % 4u == 0u) && ((reinterpret_cast<uintptr_t>(p.out) & 15u) == 0u) && (T % 4u == 0u);
+    const unsigned long long total = (unsigned long long)n * units;
+    for (unsigned long long w = warp; w < total; w += n_warps) {
+        const uint32_t rec = uint32_t(w / units), u = uint32_t(w % units);
+        const FillRec fr = p.fills[rec];
+        const float v = __uint_as_float(fr.value);
+        const uint32_t first = u * unit_px;
+        for (uint32_t q = lane * 4u; q < unit_px; q += 128u) {
+            uint32_t pix = first + q;
+            uint32_t x = fr.x + pix % T, y = fr.y + pix / T;
+            if (y >= p.height) continue;
+            float* dst = p.out + size_t(y) * p.width + x;
+            if (vec_ok && x + 3u < p.width) {
+                *reinterpret_cast<float4*>(dst) = make_float4(v, v, v, v);
+            } else {
+                for (uint32_t k = 0; k < 4u; ++k)
+                    if (x + k < p.width && (pix + k) / T == pix / T) dst[k] = v;
+            }
+        }
+    }
+}
+
+void launch_fill_2d(const FillParams& p, int blocks, cudaStream_t s) { k_fill_2d<<<blocks, 256, 0, s>>>(p); }
+
+// ---------------------------------------------------------------------------
+// Trait-level evaluators
+template <int NSLOTS>
+__global__ void __launch_bounds__(128) k_float_slice(const __grid_constant__ BulkParams p) {
+    float slots[NSLOTS];
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    for (uint64_t idx = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < p.n; idx += stride) {
+        const uint2* tape = p.tape;
+        for (uint32_t i = 0; i < p.n_ops; ++i) {
+            uint2 w = __ldg(tape + i);
+            Dec d(w.x);
+            float imm = __uint_as_float(w.y);
+            float sl = slots[d.lhs], sr = slots[d.rhs];
+            float a = d.form == F_IR ? imm : sl;
+            float b = d.form == F_RI ? imm : sr;
+            float r;
+            if (d.op == OP_MEM) {
+                if (d.form == F_RI) slots[d.out] = slots[MEM_BASE + w.y];
+                else slots[MEM_BASE + w.y] = sl;
+                continue;
+            } else if (d.op >= OP_ADD) r = f32_binary(d.op, a, b);
+            else if (d.op >= OP_NEG) r = f32_unary(d.op, sl);
+            else if (d.op == OP_COPY) r = d.form == F_RI ? imm : sl;
+            else if (d.op == OP_INPUT) r = static_cast<const float*>(p.vars[w.y])[idx];
+            else {
+                static_cast<float*>(p.outs[w.y])[idx] = sl;
+                continue;
+            }
+            slots[d.out] = r;
+        }
+    }
+}
+
+template <int NSLOTS>
+__global__ void __launch_bounds__(128) k_grad_slice(const __grid_constant__ BulkParams p) {
+    grd slots[NSLOTS];
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    for (uint64_t idx = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < p.n; idx += stride) {
+        const uint2* tape = p.tape;
+        for (uint32_t i = 0; i < p.n_ops; ++i) {
+            uint2 w = __ldg(tape + i);
+            Dec d(w.x);
+            float imm = __uint_as_float(w.y);
+            grd sl = slots[d.lhs], sr = slots[d.rhs];
+            grd a = d.form == F_IR ? gr1(imm) : sl;
+            grd b = d.form == F_RI ? gr1(imm) : sr;
+            grd r;
+            if (d.op == OP_MEM) {
+                if (d.form == F_RI) slots[d.out] = slots[MEM_BASE + w.y];
+                else slots[MEM_BASE + w.y] = sl;
+                continue;
+            } else if (d.op >= OP_ADD) {
+                if (d.op == OP_MUL && d.form == F_RI) r = gr_mul_f(sl, imm);
+                else r = gr_binary(d.op, a, b);
+            } else if (d.op >= OP_NEG) r = gr_unary(d.op, sl);
+            else if (d.op == OP_COPY) r = d.form == F_RI ? gr1(imm) : sl;
+            else if (d.op == OP_INPUT) r = static_cast<const grd*>(p.vars[w.y])[idx];
+            else {
+                static_cast<grd*>(p.outs[w.y])[idx] = sl;
+                continue;
+            }
+            slots[d.out] = r;
+        }
+    }
+}
+
+static int bulk_blocks(uint64_t n) {
+    uint64_t b = (n + 127) / 128;
+    return int(b < 1 ? 1 : (b > 148ull * 16 ? 148ull * 16 : b));
+}
+void launch_float_slice(const BulkParams& p, cudaStream_t s) {
+    if (p.n == 0) return;
+    if (p.n_slots <= 256) k_float_slice<256><<<bulk_blocks(p.n), 128, 0, s>>>(p);
+    else k_float_slice<2048><<<bulk_blocks(p.n), 128, 0, s>>>(p);
+}
+void launch_grad_slice(const BulkParams& p, cudaStream_t s) {
+    if (p.n == 0) return;
+    if (p.n_slots <= 256) k_grad_slice<256><<<bulk_blocks(p.n), 128, 0, s>>>(p);
+    else k_grad_slice<2048><<<bulk_blocks(p.n), 128, 0, s>>>(p);
+}
+
+struct ByteChoiceSink {
+    uint8_t* base;  // may be null
+    uint32_t ci = 0;
+    bool any_nonboth = false;
+    __device__ __forceinline__ void push(uint32_t c) {
+        if (base) base[ci] = uint8_t(c);
+        ++ci;
+        any_nonboth |= (c != 3u);
+    }
+};
+
+template <int NSLOTS>
+__global__ void __launch_bounds__(128) k_interval_batch(const __grid_constant__ TracingParams p) {
+    itv slots[NSLOTS];
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    for (uint64_t idx = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < p.n; idx += stride) {
+        const float* v = p.vars + idx * p.n_vars * 2;
+        float* o = p.out + idx * p.n_outputs * 2;
+        ByteChoiceSink sink;
+        sink.base = p.choices ? p.choices + idx * p.n_choices : nullptr;
+        run_interval(
+            p.tape, p.n_ops, slots, [&](uint32_t i) { return iv(v[2 * i], v[2 * i + 1]); }, sink,
+            [&](uint32_t oi, itv val) { o[2 * oi] = val.x; o[2 * oi + 1] = val.y; });
+        if (p.simplify) p.simplify[idx] = sink.any_nonboth ? 1 : 0;
+    }
+}
+
+template <int NSLOTS>
+__global__ void __launch_bounds__(128) k_point_batch(const __grid_constant__ TracingParams p) {
+    float slots[NSLOTS];
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    for (uint64_t idx = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < p.n; idx += stride) {
+        const float* v = p.vars + idx * p.n_vars;
+        float* o = p.out + idx * p.n_outputs;
+        ByteChoiceSink sink;
+        sink.base = p.choices ? p.choices + idx * p.n_choices : nullptr;
+        for (uint32_t i = 0; i < p.n_ops; ++i) {
+            uint2 w = __ldg(p.tape + i);
+            Dec d(w.x);
+            float imm = __uint_as_float(w.y);
+            float sl = slots[d.lhs], sr = slots[d.rhs];
+            float a = d.form == F_IR ? imm : sl;
+            float b = d.form == F_RI ? imm : sr;
+            float r;
+            if (d.op == OP_MEM) {
+                if (d.form == F_RI) slots[d.out] = slots[MEM_BASE + w.y];
+                else slots[MEM_BASE + w.y] = sl;
+                continue;
+            } else if (d.op >= OP_MIN) {
+                r = f32_binary(d.op, a, b);
+                sink.push(f32_choice(d.op, a, b));
+            } else if (d.op >= OP_ADD) r = f32_binary(d.op, a, b);
+            else if (d.op >= OP_NEG) r = f32_unary(d.op, sl);
+            else if (d.op == OP_COPY) r = d.form == F_RI ? imm : sl;
+            else if (d.op == OP_INPUT) r = v[w.y];
+            else { o[w.y] = sl; continue; }
+            slots[d.out] = r;
+        }
+        if (p.simplify) p.simplify[idx] = sink.any_nonboth ? 1 : 0;
+    }
+}
+
+void launch_interval_batch(const TracingParams& p, cudaStream_t s) {
+    if (p.n == 0) return;
+    if (p.n_slots <= 256) k_interval_batch<256><<<bulk_blocks(p.n), 128, 0, s>>>(p);
+    else k_interval_batch<2048><<<bulk_blocks(p.n), 128, 0, s>>>(p);
+}
+void launch_point_batch(const TracingParams& p, cudaStream_t s) {
+    if (p.n == 0) return;
+    if (p.n_slots <= 256) k_point_batch<256><<<bulk_blocks(p.n), 128, 0, s>>>(p);
+    else k_point_batch<2048><<<bulk_blocks(p.n), 128, 0, s>>>(p);
+}
+
+__global__ void k_simplify_single(const __grid_constant__ SimplifyParams p) {
+    __shared__ uint32_t live_s[8][32];
+    const int lane = threadIdx.x;
+    ByteChoiceSource src;
+    src.base = p.choices;
+    src.ci = p.n_choices;
+    uint32_t n_dev = 0, ref_len = 0, nch = 0;
+    simplify_lane(p.parent, p.n_ops, lane == 0, live_s, lane, src, p.out + p.n_ops, n_dev, ref_len, nch);
+    if (lane == 0) {
+        p.result[0] = n_dev;
+        p.result[1] = ref_len;
+        p.result[2] = nch;
+    }
+}
+void launch_simplify_single(const SimplifyParams& p, cudaStream_t s) { k_simplify_single<<<1, 32, 0, s>>>(p); }
+
+}  // namespace fdev

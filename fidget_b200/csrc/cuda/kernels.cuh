@@ -1,0 +1,150 @@
+// Kernel-side data structures shared between kernels.cu and capi.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dev_ops.cuh"
+
+namespace fdev {
+
+constexpr int MAX_LEVELS = 8;
+constexpr int WARPS_PER_BLOCK = 4;          // interval kernels
+constexpr int REG_SLOTS = 256;              // register slots of the fast interpreters
+
+// A tape living in the device arena (units of uint2 clauses)
+struct TapeRef {
+    const uint2* ptr;     // first clause (device memory: a root tape buffer or the arena)
+    uint32_t n_ops;       // device clauses
+    uint32_t ref_len;     // RegTape::len() of the reference's equivalent tape
+    uint32_t n_choices;   // choice clauses (== reference choice_count)
+    uint32_t pad;
+};
+
+// One tile that survived the previous level ("ambiguous"), plus the tape its
+// children are evaluated with.
+struct TileJob {
+    uint32_t x, y, z;     // corner in pixels/voxels
+    uint32_t pad;
+    TapeRef tape;
+};  // 40 bytes
+
+struct FillRec { uint32_t x, y, value; };  // 2D fill: corner + RawDistancePixel bits
+
+struct Stats {
+    unsigned long long evaluated[MAX_LEVELS];
+    unsigned long long filled_inside[MAX_LEVELS];
+    unsigned long long filled_outside[MAX_LEVELS];
+    unsigned long long ambiguous[MAX_LEVELS];
+    unsigned long long simplified[MAX_LEVELS];
+    unsigned long long pixels;
+    unsigned long long grads;
+    unsigned long long culled[MAX_LEVELS];
+};
+
+// Device-side counters of one render call
+struct Counters {
+    uint32_t n_jobs[MAX_LEVELS + 1];   // n_jobs[l] = tiles queued FOR level l (parents whose children are evaluated at l)
+    uint32_t n_fills[MAX_LEVELS];      // 2D fill records produced by level l
+    uint32_t cursor[MAX_LEVELS + 2];   // dynamic work cursors (one per kernel)
+    uint32_t error;                    // bit 0: arena exhausted, bit 1: list overflow
+    uint32_t pad;
+    unsigned long long arena_top;      // bump pointer (clauses)
+};
+
+struct LevelParams {
+    int level;                 // index into tile sizes
+    uint32_t tile;             // edge of the tiles evaluated by this launch
+    uint32_t n_axis;           // children per axis of each parent job (level > 0)
+    uint32_t is_last;          // children are leaf tiles
+    uint32_t pixel_perfect;
+    // level 0 enumerates root tiles itself
+    uint32_t root_mode;
+    uint32_t roots_x, roots_y, roots_z;     // root grid
+    uint32_t root_x0, root_y0, root_z0;     // origin of the root grid (pixels)
+    TapeRef root_tape;
+    // image
+    uint32_t width, height, depth;
+    float z2d;
+    Mat4 mat;
+    // lists
+    const TileJob* jobs_in;
+    TileJob* jobs_out;
+    uint32_t cap_out;
+    FillRec* fills;
+    uint32_t cap_fills;
+    // arena
+    uint2* arena;
+    unsigned long long arena_cap;   // clauses
+    // scratch: per-warp choice words [choice_words][32]
+    uint32_t* choice_scratch;
+    uint32_t choice_words;          // words per lane
+    Counters* ctr;
+    Stats* stats;
+    // 3D
+    uint32_t* heightmap;            // width*height depth values (atomicMax)
+    uint32_t n_vars;
+    int var_x, var_y, var_z;
+};
+
+struct PixelParams {
+    uint32_t tile;             // leaf tile edge
+    uint32_t width, height;
+    float z2d;
+    Mat4 mat;
+    const TileJob* jobs;
+    float* out;
+    Counters* ctr;
+    int list;                  // which n_jobs entry holds the leaf count
+    int cursor;
+    Stats* stats;
+    int var_x, var_y, var_z;
+};
+
+struct FillParams {
+    uint32_t tile, width, height;
+    const FillRec* fills;
+    const uint32_t* n_fills;
+    float* out;
+};
+
+// launchers (kernels.cu)
+void launch_interval_level_2d(const LevelParams& p, int blocks, cudaStream_t s);
+void launch_pixels_2d(const PixelParams& p, int blocks, cudaStream_t s);
+void launch_fill_2d(const FillParams& p, int blocks, cudaStream_t s);
+
+// trait-level evaluators
+struct BulkParams {
+    const uint2* tape;
+    uint32_t n_ops;
+    uint32_t n_vars, n_outputs;
+    uint32_t n_slots;           // 256 + mem_count
+    uint64_t n;
+    const void* const* vars;    // device array of device pointers (n_vars)
+    void* const* outs;          // device array of device pointers (n_outputs)
+};
+void launch_float_slice(const BulkParams& p, cudaStream_t s);
+void launch_grad_slice(const BulkParams& p, cudaStream_t s);
+
+struct TracingParams {
+    const uint2* tape;
+    uint32_t n_ops, n_vars, n_outputs, n_choices, n_slots;
+    uint64_t n;
+    const float* vars;   // interval: [n][n_vars][2]; point: [n][n_vars]
+    float* out;          // interval: [n][n_outputs][2]; point: [n][n_outputs]
+    uint8_t* choices;    // [n][n_choices] or null
+    uint8_t* simplify;   // [n] or null
+};
+void launch_interval_batch(const TracingParams& p, cudaStream_t s);
+void launch_point_batch(const TracingParams& p, cudaStream_t s);
+
+struct SimplifyParams {
+    const uint2* parent;
+    uint32_t n_ops, parent_ref_len;
+    const uint8_t* choices;   // [n_choices] bytes
+    uint32_t n_choices;
+    uint2* out;               // capacity n_ops; child occupies the TAIL
+    uint32_t* result;         // {n_dev, ref_len, n_choices_child}
+};
+void launch_simplify_single(const SimplifyParams& p, cudaStream_t s);
+
+}  // namespace fdev

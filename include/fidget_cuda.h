@@ -1,0 +1,196 @@
+/* libfidget_cuda -- B200 (sm_100a) backend for Fidget's tape-evaluation hot path.
+ *
+ * C ABI, plain pointers and sizes only.  Every entry point cites the reference
+ * interface it replaces (paths relative to the mkeeter/fidget checkout);
+ * INTEGRATION.md shows the Rust `extern "C"` block and the `CudaFunction`
+ * shim a maintainer would add on the reference side.
+ *
+ * Conventions
+ *  - every function returns FC_OK (0) or a negative fc_status; nothing throws
+ *    or aborts across the boundary.  fc_last_error() returns a message for the
+ *    most recent failure on the calling thread.
+ *  - handles are opaque.  fc_tape is reference counted (Arc semantics, like
+ *    `GenericVmTape(Arc<VmData>)`, fidget-core/src/vm/mod.rs:47-48).
+ *  - an fc_eval owns its scratch + output buffers and one CUDA stream; use one
+ *    per thread, like the reference's evaluators (eval/bulk.rs:23-58).
+ *  - pointers marked "host or device" are classified with
+ *    cudaPointerGetAttributes; device (or managed) memory is used in place.
+ *  - numerics: IEEE f32, round-to-nearest, no FMA contraction, denormals kept
+ *    (the library is built with -fmad=false -prec-div=true -prec-sqrt=true
+ *    -ftz=false).  add/sub/mul/div/sqrt/neg/abs/min/max/square/floor/ceil/
+ *    round/mod and all comparisons are bit-identical to the reference VM;
+ *    sin/cos/tan/asin/acos/atan/atan2/exp/ln use CUDA libdevice (<= 2 ulp).
+ */
+#ifndef FIDGET_CUDA_H
+#define FIDGET_CUDA_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum fc_status {
+    FC_OK = 0,
+    FC_ERR_INVALID = -1,      /* bad argument / malformed bytecode */
+    FC_ERR_CUDA = -2,         /* CUDA runtime error (message has the detail) */
+    FC_ERR_UNSUPPORTED = -3,  /* valid input the device path cannot take (e.g. spilled tape in a renderer) */
+    FC_ERR_ARENA = -4,        /* tape arena exhausted during on-device simplification */
+    FC_ERR_NO_DEVICE = -5     /* no usable CUDA device; there is NO CPU fallback */
+} fc_status;
+
+typedef struct fc_ctx fc_ctx;    /* one GPU + stream + scratch arenas */
+typedef struct fc_tape fc_tape;  /* device-resident tape */
+typedef struct fc_eval fc_eval;  /* per-thread evaluator scratch */
+
+const char* fc_last_error(void);
+/* Library/ABI version; bumped on any signature change */
+uint32_t fc_abi_version(void);
+
+/* ---- lifecycle ---------------------------------------------------------- */
+int32_t fc_ctx_create(int32_t device, fc_ctx** out);
+void fc_ctx_destroy(fc_ctx* ctx);
+/* Enqueue all subsequent work of this context on `cuda_stream` (a
+ * cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream); NULL restores
+ * the context's own stream. */
+int32_t fc_ctx_set_stream(fc_ctx* ctx, void* cuda_stream);
+/* Wait for enqueued work and report deferred device-side errors
+ * (FC_ERR_ARENA, ...). */
+int32_t fc_ctx_synchronize(fc_ctx* ctx);
+/* Size of the tape arena used by on-device simplification (bytes; default
+ * 1 GiB).  Takes effect at the next render call. */
+int32_t fc_ctx_set_arena_bytes(fc_ctx* ctx, uint64_t bytes);
+
+/* ---- tapes -------------------------------------------------------------- */
+/* `words` is exactly what fidget_bytecode::Bytecode::new emits
+ * (fidget-bytecode/src/lib.rs:203-332): [0xFFFFFFFF,0] op pairs ...
+ * [0xFFFFFFFF,0xFFFFFFFF]; reg_count / mem_count from Bytecode::{reg_count,
+ * mem_count}; n_vars = VarMap::len, n_outputs = VmData::output_count,
+ * choice_count = VmData::choice_count (checked against the words). */
+int32_t fc_tape_create(fc_ctx* ctx, const uint32_t* words, size_t n_words, uint8_t reg_count,
+                       uint32_t mem_count, uint32_t n_vars, uint32_t n_outputs, uint32_t choice_count,
+                       fc_tape** out);
+int32_t fc_tape_retain(fc_tape* tape);
+int32_t fc_tape_release(fc_tape* tape);
+
+typedef struct fc_tape_info {
+    uint32_t n_ops;         /* clauses in the device tape */
+    uint32_t ref_len;       /* RegTape::len() of the equivalent reference tape (Function::size) */
+    uint32_t choice_count;
+    uint32_t reg_count;
+    uint32_t mem_count;
+    uint32_t n_vars;
+    uint32_t n_outputs;
+} fc_tape_info;
+int32_t fc_tape_get_info(const fc_tape* tape, fc_tape_info* info);
+/* Which input slots carry X, Y, Z (VarMap lookup of Var::X/Y/Z, shape/mod.rs:355-376;
+ * -1 = the shape does not use that axis).  Default: x=0,y=1,z=2 clipped to n_vars.
+ * The renderers feed transformed coordinates into these slots. */
+int32_t fc_tape_set_axes(fc_tape* tape, int32_t x, int32_t y, int32_t z);
+/* Copies the device tape back as bytecode words (same framing as the input;
+ * device-only alias copies appear as plain Copy clauses).  words==NULL
+ * queries the count. */
+int32_t fc_tape_read(const fc_tape* tape, uint32_t* words, size_t cap, size_t* n_words);
+
+/* ---- trait-level evaluators -------------------------------------------- */
+/* These mirror TracingEvaluator / BulkEvaluator (eval/tracing.rs:26-61,
+ * eval/bulk.rs:23-58) the way fidget-jit's raw function pointers do
+ * (fidget-jit/src/lib.rs:1058-1065,1172-1178). */
+int32_t fc_eval_create(fc_ctx* ctx, fc_eval** out);
+void fc_eval_destroy(fc_eval* e);
+
+/* VmIntervalEval::eval (vm/mod.rs:332-537).  vars: [n_vars][2] = lower,upper.
+ * out: [n_outputs][2].  choices: [choice_count] bytes (Choice as u8:
+ * 0 unknown, 1 left, 2 right, 3 both), may be NULL.  *simplify = 1 iff a
+ * trace is available (some choice != Both).  Host pointers. */
+int32_t fc_interval_eval(fc_eval* e, const fc_tape* tape, const float* vars_lo_hi, float* out_lo_hi,
+                         uint8_t* choices, uint8_t* simplify);
+/* VmPointEval::eval (vm/mod.rs:551-759) */
+int32_t fc_point_eval(fc_eval* e, const fc_tape* tape, const float* vars, float* out, uint8_t* choices,
+                      uint8_t* simplify);
+/* n independent boxes in one launch (one lane per box; what the octree
+ * sampler and the conformance tests use).  vars: [n][n_vars][2];
+ * out: [n][n_outputs][2]; choices: [n][choice_count] or NULL;
+ * simplify: [n] or NULL.  Host or device pointers. */
+int32_t fc_interval_eval_batch(fc_eval* e, const fc_tape* tape, const float* vars, uint64_t n, float* out,
+                               uint8_t* choices, uint8_t* simplify);
+/* VmFloatSliceEval::eval (vm/mod.rs:800-1085): vars[i] -> n floats (SoA),
+ * out[o] -> n floats.  The arrays of pointers are host arrays; the pointed-to
+ * buffers may be host or device. */
+int32_t fc_float_slice_eval(fc_eval* e, const fc_tape* tape, const float* const* vars, float* const* out,
+                            uint64_t n);
+typedef struct fc_grad { float v, dx, dy, dz; } fc_grad; /* types/grad.rs:2-13, #[repr(C)] */
+/* VmGradSliceEval::eval (vm/mod.rs:1097-1396) */
+int32_t fc_grad_slice_eval(fc_eval* e, const fc_tape* tape, const fc_grad* const* vars,
+                           fc_grad* const* out, uint64_t n);
+/* VmData::simplify (vm/data.rs:123-318) run on the device for one trace.
+ * The child keeps the parent's register assignment (no re-allocation), is
+ * value-identical to the reference's child, and reports the reference's
+ * child length in fc_tape_info.ref_len.  Parent must not use memory slots. */
+int32_t fc_simplify(fc_eval* e, const fc_tape* parent, const uint8_t* choices, size_t n_choices,
+                    fc_tape** child);
+
+/* ---- fused renderers (the measured path) -------------------------------- */
+#define FC_MAX_TILE_LEVELS 8
+#define FC_FLAG_ASYNC 1u        /* enqueue only; errors surface in fc_ctx_synchronize */
+#define FC_FLAG_TIMING 2u       /* record per-stage CUDA events (fc_render_stats.stage_ms) */
+
+typedef struct fc_render2d_cfg {
+    uint32_t width, height;
+    float mat[16];              /* row-major 4x4, screen -> model: RenderConfig::mat() embedded as in
+                                   fidget-raster/src/pixel.rs:283-287 */
+    float z;                    /* pixel::RenderConfig::z */
+    uint32_t pixel_perfect;     /* pixel::RenderConfig::pixel_perfect */
+    uint32_t n_tile_sizes;      /* 0 => the VM default {128,32,8} (vm/mod.rs:254-256) */
+    uint32_t tile_sizes[FC_MAX_TILE_LEVELS];
+    uint32_t flags;
+    /* Y band [row_begin,row_end) of root-tile rows to render (multi-GPU
+     * sharding); row_end = 0 means all rows. */
+    uint32_t root_row_begin, root_row_end;
+} fc_render2d_cfg;
+
+typedef struct fc_geometry_pixel { float normal[3]; uint32_t depth; } fc_geometry_pixel; /* voxel.rs:126-134 */
+
+typedef struct fc_render3d_cfg {
+    uint32_t width, height, depth;
+    float mat[16];              /* row-major 4x4: voxel::RenderConfig::mat() (voxel.rs:107-109) */
+    uint32_t n_tile_sizes;      /* 0 => {128,64,32,16,8} (vm/mod.rs:250-252) */
+    uint32_t tile_sizes[FC_MAX_TILE_LEVELS];
+    uint32_t flags;
+    /* Z slab [z_begin,z_end) in voxels (multiples of tile_sizes[0]);
+     * z_end = 0 means the whole depth. */
+    uint32_t z_begin, z_end;
+} fc_render3d_cfg;
+
+typedef struct fc_render_stats {
+    uint64_t evaluated[FC_MAX_TILE_LEVELS];      /* interval evaluations per level */
+    uint64_t filled_inside[FC_MAX_TILE_LEVELS];
+    uint64_t filled_outside[FC_MAX_TILE_LEVELS];
+    uint64_t ambiguous[FC_MAX_TILE_LEVELS];
+    uint64_t simplified[FC_MAX_TILE_LEVELS];     /* simplifications kept (shorter than parent) */
+    uint64_t pixels;                             /* points shaded by the bulk kernel */
+    uint64_t grads;                              /* points shaded by the gradient kernel */
+    uint64_t arena_bytes_used;
+    uint32_t kernel_launches;
+    float stage_ms[16];                          /* FC_FLAG_TIMING: interval levels 0..7, then [8]=fill,
+                                                    [9]=bulk f32, [10]=grad, [11]=merge, [15]=total */
+} fc_render_stats;
+
+/* pixel::render (fidget-raster/src/pixel.rs:452-492).  out: width*height
+ * RawDistancePixel bit patterns as f32, row-major; host or device. */
+int32_t fc_render2d(fc_ctx* ctx, const fc_tape* tape, const fc_render2d_cfg* cfg, float* out,
+                    fc_render_stats* stats /* may be NULL */);
+/* voxel::render (fidget-raster/src/voxel.rs:500-553).  out: width*height
+ * GeometryPixel; host or device. */
+int32_t fc_render3d(fc_ctx* ctx, const fc_tape* tape, const fc_render3d_cfg* cfg, fc_geometry_pixel* out,
+                    fc_render_stats* stats /* may be NULL */);
+/* Per-pixel merge of `n_slabs` slab images (each width*height, device
+ * pointers, Z-ordered) into `out`, applying the final depth clamp of
+ * voxel.rs:535-546.  Used after the all-gather in multi-GPU renders. */
+int32_t fc_merge_slabs(fc_ctx* ctx, const fc_geometry_pixel* const* slabs, uint32_t n_slabs,
+                       uint32_t width, uint32_t height, uint32_t depth, fc_geometry_pixel* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FIDGET_CUDA_H */

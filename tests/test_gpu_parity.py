@@ -1,0 +1,147 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle
+on identical tapes and inputs."""
+import numpy as np
+import pytest
+
+import fidget_b200 as fb
+from conftest import model_text, same_f32
+
+pytestmark = pytest.mark.gpu
+
+EXACT_MODELS = ["prospero.vm", "hi.vm", "quarter.vm", "colonnade.vm", "tanglecube.vm"]
+
+
+def _pair(orc, cuda, name, n_regs=255):
+    text = model_text(name)
+    return orc.Tape.from_vm(text, n_regs), fb.CudaShape.from_vm(cuda, text, n_regs)
+
+
+def _points(n, nv, seed=0):
+    rng = np.random.default_rng(seed)
+    return [rng.uniform(-1, 1, n).astype(np.float32) for _ in range(nv)]
+
+
+@pytest.mark.parametrize("name", EXACT_MODELS)
+def test_float_slice_bit_exact(orc, cuda, name):
+    ot, gs = _pair(orc, cuda, name)
+    pts = _points(4099, ot.n_vars)
+    assert same_f32(gs.float_slice_eval(pts), ot.float_slice_eval(pts))
+
+
+def test_float_slice_bear_tolerance(orc, cuda):
+    ot, gs = _pair(orc, cuda, "bear.vm")
+    pts = _points(4099, ot.n_vars, 1)
+    g, o = gs.float_slice_eval(pts), ot.float_slice_eval(pts)
+    assert np.array_equal(np.isnan(g), np.isnan(o))
+    m = ~np.isnan(o)
+    assert np.all(np.abs(g[m] - o[m]) <= 1e-5 * np.maximum(1.0, np.abs(o[m])))  # north_star tolerance
+
+
+@pytest.mark.parametrize("n", [0, 1, 3, 4, 7, 8, 9, 31, 33])
+def test_float_slice_sizes(orc, cuda, n):
+    ot, gs = _pair(orc, cuda, "hi.vm")
+    pts = _points(n, ot.n_vars, n)
+    assert same_f32(gs.float_slice_eval(pts), ot.float_slice_eval(pts))
+
+
+def _boxes(n, nv, seed=0, scale=1.0):
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-1, 1, (n, nv)).astype(np.float32)
+    w = (rng.uniform(0, 1, (n, nv)) ** 3 * scale).astype(np.float32)
+    return np.stack([c - w, c + w], axis=-1).astype(np.float32)
+
+
+@pytest.mark.parametrize("name", EXACT_MODELS)
+def test_interval_bit_exact_with_choices(orc, cuda, name):
+    ot, gs = _pair(orc, cuda, name)
+    boxes = _boxes(257, ot.n_vars, 3)
+    out, ch, simp = gs.interval_eval_batch(boxes, want_choices=True)
+    for i in range(boxes.shape[0]):
+        o, oc, os_ = ot.interval_eval(boxes[i])
+        assert same_f32(out[i, 0], o), (name, i)
+        assert np.array_equal(ch[i], oc), (name, i)
+        assert bool(simp[i]) == os_
+
+
+@pytest.mark.parametrize("name", ["prospero.vm", "hi.vm", "colonnade.vm", "bear.vm"])
+def test_simplify_matches_reference_length_and_values(orc, cuda, name):
+    ot, gs = _pair(orc, cuda, name)
+    boxes = _boxes(24, ot.n_vars, 5, scale=0.3)
+    for i in range(boxes.shape[0]):
+        _, oc, os_ = ot.interval_eval(boxes[i])
+        if not os_:
+            continue
+        child_o = ot.simplify(oc)
+        child_g = gs.simplify(oc)
+        assert child_g.size() == child_o.size, (name, i)          # Function::size() of the child
+        assert child_g.choice_count == child_o.choice_count
+        # value parity of the simplified tapes inside the box
+        rng = np.random.default_rng(i)
+        pts = [rng.uniform(boxes[i, v, 0], boxes[i, v, 1], 513).astype(np.float32) for v in range(ot.n_vars)]
+        g, o = child_g.float_slice_eval(pts), child_o.float_slice_eval(pts)
+        if name == "bear.vm":
+            assert np.allclose(g, o, rtol=1e-5, atol=1e-5, equal_nan=True)
+        else:
+            assert same_f32(g, o)
+        # second-generation simplification keeps agreeing
+        sub = boxes[i].copy()
+        mid = (sub[:, 0] + sub[:, 1]) / 2
+        sub[:, 1] = mid
+        o2, oc2, os2 = child_o.interval_eval(sub)
+        g2, gc2, gs2 = child_g.interval_eval(sub)
+        if name == "bear.vm":  # libdevice vs glibc transcendentals: tolerance, not bits
+            assert np.allclose(g2[0], o2, rtol=1e-5, atol=1e-5, equal_nan=True)
+            continue
+        assert same_f32(g2[0], o2) and np.array_equal(gc2, oc2) and gs2 == os2
+        if os2:
+            assert child_g.simplify(gc2).size() == child_o.simplify(oc2).size
+
+
+HI_32 = """
+.................#..............
+.................#..............
+.................#..............
+.................#..........##..
+.................#..........##..
+.................#..............
+.................#..............
+.................######.....##..
+.................###..##....##..
+.................##....##...##..
+.................#......#...##..
+.................#......#...##..
+.................#......#...##..
+.................#......#...##..
+.................#......#...##..
+""".strip().split("\n") + ["." * 32] * 17
+
+
+def test_render2d_hi_golden(cuda):
+    # fidget/tests/pixel_render.rs:70-106 (check_hi)
+    gs = fb.CudaShape.from_vm(cuda, model_text("hi.vm"))
+    img = fb.render2d(gs, fb.RenderConfig2D(32, 32))
+    rows = ["".join("#" if b else "." for b in r) for r in fb.pixel_inside(img)]
+    assert rows == HI_32
+
+
+@pytest.mark.parametrize("name,size", [("hi.vm", 256), ("quarter.vm", 256), ("prospero.vm", 512),
+                                       ("colonnade.vm", 256), ("prospero.vm", 1000)])
+def test_render2d_matches_oracle(orc, cuda, name, size):
+    ot, gs = _pair(orc, cuda, name)
+    o_img, o_st = orc.render2d(ot, size, size, threads=8)
+    g_img, g_st = fb.render2d(gs, fb.RenderConfig2D(size, size), stats=True)
+    for k in ("evaluated", "filled_inside", "filled_outside", "ambiguous", "simplified"):
+        assert g_st[k] == o_st[k], k                             # tile masks, level by level
+    assert g_st["pixels"] == o_st["pixels"]
+    assert np.array_equal(g_img.view(np.uint32), o_img.view(np.uint32))   # pixel-exact incl. fill encodings
+
+
+def test_render2d_prospero_4096_full(orc, cuda):
+    """BASELINE config 2 at full size: bit-identical image and tile census."""
+    ot, gs = _pair(orc, cuda, "prospero.vm")
+    o_img, o_st = orc.render2d(ot, 4096, 4096, threads=0 or 8)
+    g_img, g_st = fb.render2d(gs, fb.RenderConfig2D(4096, 4096), stats=True)
+    for k in ("evaluated", "filled_inside", "filled_outside", "ambiguous", "simplified"):
+        assert g_st[k] == o_st[k], k
+    assert np.array_equal(g_img.view(np.uint32), o_img.view(np.uint32))
+    assert np.array_equal(fb.pixel_inside(g_img), orc.pixel_inside(o_img))
