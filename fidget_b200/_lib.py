@@ -72,7 +72,7 @@ CUDA_API = {
     "fc_abi_version": (_u32, []),
     "fc_ctx_create": (_i32, [_i32, _P(_vp)]),
     "fc_ctx_destroy": (None, [_vp]),
-    "fc_ctx_set_stream": (_i32, [_vp, _vp]),
+    "fc_ctx_set_stream": (_i32, [_vp, _vp, _i32]),
     "fc_ctx_synchronize": (_i32, [_vp]),
     "fc_ctx_set_arena_bytes": (_i32, [_vp, _u64]),
     "fc_tape_create": (_i32, [_vp, _P(_u32), C.c_size_t, _u8, _u32, _u32, _u32, _u32, _P(_vp)]),

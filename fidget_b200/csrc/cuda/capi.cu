@@ -1,4 +1,5 @@
 // Host orchestration + C ABI of libfidget_cuda (include/fidget_cuda.h).
+#include <algorithm>
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
@@ -81,7 +82,120 @@ struct fc_tape {
     std::vector<uint2> host;  // copy of the device clauses
     fc_tape_info info{};
     int ax[3] = {-1, -1, -1};  // input slots of X, Y, Z
+    // cooperative level-0 schedule (empty when the tape is unsuitable)
+    CoopRec* d_recs = nullptr;
+    uint32_t* d_wave_start = nullptr;
+    uint32_t n_waves = 0, tail_begin = 0, tail_end = 0;
+    std::vector<CoopSeg> segs;
 };
+
+// Dependency-wave schedule of a register tape: value id = position of the
+// defining clause; clauses are bucketed by dependency depth, sorted by opcode
+// inside a bucket (keeps warps convergent); the trailing single-clause
+// buckets form the serial tail.
+static bool build_schedule(const std::vector<uint2>& cl, std::vector<CoopRec>& recs,
+                           std::vector<uint32_t>& wave_start, uint32_t& tail_begin, std::vector<CoopSeg>& segs) {
+    const size_t n = cl.size();
+    if (n == 0 || n >= COOP_NONE) return false;
+    std::vector<int> regdef(256, -1);
+    std::vector<uint32_t> depth(n, 0);
+    std::vector<CoopRec> byp(n);
+    uint32_t ci = 0, max_depth = 0;
+    for (size_t p = 0; p < n; ++p) {
+        uint32_t x = cl[p].x, dop = x & 0xff, op = dop >> 2, form = dop & 3, out = (x >> 8) & 0xff,
+                 lhs = (x >> 16) & 0xff, rhs = x >> 24;
+        if (op == OP_MEM) return false;
+        CoopRec r;
+        r.x = x; r.y = cl[p].y; r.ia = COOP_NONE; r.ib = COOP_NONE; r.p = uint16_t(p); r.cidx = 0;
+        bool use_l = false, use_r = false;
+        if (op == OP_OUTPUT) use_l = true;
+        else if (op == OP_INPUT) {}
+        else if (op == OP_COPY) use_l = (form != F_RI);
+        else if (op_is_unary(op)) use_l = true;
+        else { use_l = (form != F_IR); use_r = (form != F_RI); }
+        uint32_t d = 0;
+        if (use_l) { if (regdef[lhs] < 0) return false; r.ia = uint16_t(regdef[lhs]); d = std::max(d, depth[r.ia] + 1); }
+        if (use_r) { if (regdef[rhs] < 0) return false; r.ib = uint16_t(regdef[rhs]); d = std::max(d, depth[r.ib] + 1); }
+        if (op_is_choice(op)) r.cidx = uint16_t(ci++);
+        if (ci >= COOP_NONE) return false;
+        depth[p] = d;
+        max_depth = std::max(max_depth, d);
+        if (op != OP_OUTPUT) regdef[out] = int(p);
+        byp[p] = r;
+    }
+    std::vector<std::vector<uint32_t>> levels(max_depth + 1);
+    for (size_t p = 0; p < n; ++p) levels[depth[p]].push_back(uint32_t(p));
+    size_t first_tail = levels.size();
+    while (first_tail > 0 && levels[first_tail - 1].size() == 1) --first_tail;
+    recs.clear();
+    wave_start.assign(1, 0);
+    for (size_t l = 0; l < first_tail; ++l) {
+        auto& v = levels[l];
+        std::stable_sort(v.begin(), v.end(), [&](uint32_t a, uint32_t b) { return (cl[a].x & 0xff) < (cl[b].x & 0xff); });
+        for (uint32_t p : v) recs.push_back(byp[p]);
+        wave_start.push_back(uint32_t(recs.size()));
+    }
+    tail_begin = uint32_t(recs.size());
+    for (size_t l = first_tail; l < levels.size(); ++l) recs.push_back(byp[levels[l][0]]);
+
+    // Cut the tail into serial runs and min/max chains (see CoopSeg)
+    std::vector<uint32_t> idx_of_pos(n, 0);
+    for (size_t i = 0; i < recs.size(); ++i) idx_of_pos[recs[i].p] = uint32_t(i);
+    segs.clear();
+    const uint32_t tend = uint32_t(recs.size());
+    auto chain_op = [&](uint32_t i) -> uint32_t {  // returns opcode if rec i can extend a chain, else 0
+        if (i == 0 || i <= tail_begin) return 0;
+        const CoopRec& r = recs[i];
+        uint32_t dop = r.x & 0xff, op = dop >> 2, form = dop & 3;
+        if ((op != OP_MIN && op != OP_MAX) || form != F_RR) return 0;
+        uint16_t pp = recs[i - 1].p;
+        if ((r.ia == pp) == (r.ib == pp)) return 0;
+        return op;
+    };
+    uint32_t i = tail_begin, serial_start = tail_begin;
+    auto flush_serial = [&](uint32_t upto) {
+        if (upto > serial_start) segs.push_back(CoopSeg{serial_start, upto, 0});
+        serial_start = upto;
+    };
+    while (i < tend) {
+        uint32_t op = chain_op(i);
+        if (!op) { ++i; continue; }
+        uint32_t j = i;
+        while (j < tend && chain_op(j) == op) {
+            const CoopRec& r = recs[j];
+            uint16_t pp = recs[j - 1].p;
+            uint16_t side = (r.ia == pp) ? r.ib : r.ia;
+            if (idx_of_pos[side] >= i) break;   // the side must be computed before the run starts
+            ++j;
+        }
+        if (j - i >= 8 && segs.size() + 3 <= size_t(COOP_MAX_SEGS)) {
+            flush_serial(i);
+            segs.push_back(CoopSeg{i, j, 1});
+            serial_start = j;
+            i = j;
+        } else {
+            i = std::max(j, i + 1);
+        }
+    }
+    flush_serial(tend);
+    return segs.size() <= size_t(COOP_MAX_SEGS);
+}
+
+static void upload_schedule(fc_tape* t) {
+    std::vector<CoopRec> recs;
+    std::vector<uint32_t> ws;
+    uint32_t tb = 0;
+    if (!build_schedule(t->host, recs, ws, tb, t->segs)) return;
+    if (cudaMalloc(&t->d_recs, recs.size() * sizeof(CoopRec)) != cudaSuccess) { t->d_recs = nullptr; cudaGetLastError(); return; }
+    if (cudaMalloc(&t->d_wave_start, ws.size() * 4) != cudaSuccess) {
+        cudaFree(t->d_recs); t->d_recs = nullptr; cudaGetLastError(); return;
+    }
+    cudaMemcpy(t->d_recs, recs.data(), recs.size() * sizeof(CoopRec), cudaMemcpyHostToDevice);
+    cudaMemcpy(t->d_wave_start, ws.data(), ws.size() * 4, cudaMemcpyHostToDevice);
+    t->n_waves = uint32_t(ws.size() - 1);
+    t->tail_begin = tb;
+    t->tail_end = uint32_t(recs.size());
+}
 
 struct fc_eval {
     fc_ctx* ctx = nullptr;
@@ -206,9 +320,9 @@ void fc_ctx_destroy(fc_ctx* c) {
     delete c;
 }
 
-int32_t fc_ctx_set_stream(fc_ctx* c, void* s) {
+int32_t fc_ctx_set_stream(fc_ctx* c, void* s, int32_t use_own) {
     if (!c) return fail(FC_ERR_INVALID, "null ctx");
-    c->stream = s ? static_cast<cudaStream_t>(s) : c->own_stream;
+    c->stream = use_own ? c->own_stream : static_cast<cudaStream_t>(s);
     return FC_OK;
 }
 
@@ -266,6 +380,7 @@ int32_t fc_tape_create(fc_ctx* c, const uint32_t* words, size_t n_words, uint8_t
         delete t;
         return fail(FC_ERR_CUDA, cudaGetErrorString(e));
     }
+    upload_schedule(t);
     *out = t;
     return FC_OK;
 }
@@ -280,6 +395,8 @@ int32_t fc_tape_release(fc_tape* t) {
     if (t->refs.fetch_sub(1) == 1) {
         cudaSetDevice(t->ctx->device);
         cudaFree(t->dev);
+        if (t->d_recs) cudaFree(t->d_recs);
+        if (t->d_wave_start) cudaFree(t->d_wave_start);
         delete t;
     }
     return FC_OK;
@@ -570,10 +687,7 @@ int32_t fc_render2d(fc_ctx* c, const fc_tape* tape, const fc_render2d_cfg* cfg, 
     }
     CU(cudaMemsetAsync(c->counters.p, 0, sizeof(Counters), s));
     if (want_stats) CU(cudaMemsetAsync(c->stats.p, 0, sizeof(Stats), s));
-    if (roots_y != roots_y_all || cfg->width % T0 || cfg->height % T0) {
-        // pixels outside the rendered band keep RawDistancePixel::default() = 0.0
-        if (roots_y != roots_y_all) CU(cudaMemsetAsync(dimg, 0, img_bytes, s));
-    }
+    // (pixels outside the requested band of root rows are left untouched)
 
     AxisMap ax = axes_of(tape);
     size_t ev = 0;
@@ -613,7 +727,24 @@ int32_t fc_render2d(fc_ctx* c, const fc_tape* tape, const fc_render2d_cfg* cfg, 
             uint64_t warps = (n_roots + 31) / 32;
             blocks = int(std::min<uint64_t>((warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, uint64_t(grid_blocks)));
         }
-        launch_interval_level_2d(p, std::max(blocks, 1), s);
+        bool coop = false;
+        if (l == 0 && tape->d_recs && tape->info.n_ops >= 64 && !env_int("FIDGET_B200_NO_COOP", 0)) {
+            size_t smem = coop_smem_bytes(tape->info.n_ops, tape->info.choice_count);
+            if (smem <= 220 * 1024) {
+                p.sched.recs = tape->d_recs;
+                p.sched.wave_start = tape->d_wave_start;
+                p.sched.n_waves = tape->n_waves;
+                p.sched.tail_begin = tape->tail_begin;
+                p.sched.tail_end = tape->tail_end;
+                p.sched.n_segs = uint32_t(tape->segs.size());
+                for (size_t k = 0; k < tape->segs.size(); ++k) p.sched.segs[k] = tape->segs[k];
+                int per_sm = int(std::max<size_t>(1, std::min<size_t>(16, (227 * 1024) / (smem + 1024))));
+                int cb = int(std::min<uint64_t>(n_roots, uint64_t(c->sm_count) * per_sm));
+                CU(launch_interval_root_coop_2d(p, std::max(cb, 1), s));
+                coop = true;
+            }
+        }
+        if (!coop) launch_interval_level_2d(p, std::max(blocks, 1), s);
         ++launches;
         if (timing) CU(cudaEventRecord(get_event(c, ev++), s));
     }

@@ -51,7 +51,36 @@ struct Counters {
     unsigned long long arena_top;      // bump pointer (clauses)
 };
 
+// Cooperative level-0 schedule (built on the host at fc_tape_create): the root
+// tape in SSA form (value id = position of the defining clause), clauses
+// grouped into dependency waves; a trailing run of single-clause waves is the
+// serial tail.
+constexpr int COOP_THREADS = 128;
+constexpr uint32_t COOP_NONE = 0xFFFFu;
+struct CoopRec {
+    uint32_t x, y;        // the device clause
+    uint16_t ia, ib;      // defining positions of the lhs / rhs register operands (COOP_NONE: immediate/unused)
+    uint16_t p;           // position of this clause in the tape (== id of the value it defines)
+    uint16_t cidx;        // choice index (choice clauses only)
+};
+// The tail is cut into segments: SERIAL runs are executed by one thread,
+// CHAIN runs (>= 8 consecutive min- or max-clauses, each combining the
+// previous clause's result with a value computed before the run) are
+// evaluated with a block-wide prefix scan: min/max of intervals is exactly
+// associative, and the choices follow from the prefix values.
+struct CoopSeg { uint32_t begin, end, chain; };
+constexpr int COOP_MAX_SEGS = 16;
+struct CoopSched {
+    const CoopRec* recs;
+    const uint32_t* wave_start;   // [n_waves + 1] offsets into recs
+    uint32_t n_waves;
+    uint32_t tail_begin, tail_end;
+    uint32_t n_segs;
+    CoopSeg segs[COOP_MAX_SEGS];
+};
+
 struct LevelParams {
+    CoopSched sched;
     int level;                 // index into tile sizes
     uint32_t tile;             // edge of the tiles evaluated by this launch
     uint32_t n_axis;           // children per axis of each parent job (level > 0)
@@ -109,6 +138,8 @@ struct FillParams {
 
 // launchers (kernels.cu)
 void launch_interval_level_2d(const LevelParams& p, int blocks, cudaStream_t s);
+size_t coop_smem_bytes(uint32_t n_ops, uint32_t n_choices);
+cudaError_t launch_interval_root_coop_2d(const LevelParams& p, int blocks, cudaStream_t s);
 void launch_pixels_2d(const PixelParams& p, int blocks, cudaStream_t s);
 void launch_fill_2d(const FillParams& p, int blocks, cudaStream_t s);
 

@@ -62,7 +62,11 @@ class CudaContext:
         self.close()
 
     def set_stream(self, cuda_stream: int | None):
-        _ck(self._lib.fc_ctx_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+        """Run on the given cudaStream_t handle (0 = CUDA default stream); None = the context's own stream."""
+        if cuda_stream is None:
+            _ck(self._lib.fc_ctx_set_stream(self._h, None, 1))
+        else:
+            _ck(self._lib.fc_ctx_set_stream(self._h, C.c_void_p(cuda_stream), 0))
 
     def synchronize(self):
         _ck(self._lib.fc_ctx_synchronize(self._h))

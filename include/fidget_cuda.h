@@ -51,9 +51,9 @@ uint32_t fc_abi_version(void);
 int32_t fc_ctx_create(int32_t device, fc_ctx** out);
 void fc_ctx_destroy(fc_ctx* ctx);
 /* Enqueue all subsequent work of this context on `cuda_stream` (a
- * cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream); NULL restores
- * the context's own stream. */
-int32_t fc_ctx_set_stream(fc_ctx* ctx, void* cuda_stream);
+ * cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream; NULL is the
+ * CUDA default stream).  use_own != 0 restores the context's own stream. */
+int32_t fc_ctx_set_stream(fc_ctx* ctx, void* cuda_stream, int32_t use_own);
 /* Wait for enqueued work and report deferred device-side errors
  * (FC_ERR_ARENA, ...). */
 int32_t fc_ctx_synchronize(fc_ctx* ctx);

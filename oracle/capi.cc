@@ -95,6 +95,10 @@ int32_t orc_grad_slice_eval(const orc_tape* t, const float* const* vars, float* 
 int32_t orc_simplify(const orc_tape* t, const uint8_t* choices, size_t n, orc_tape** out) {
     ORC_TRY(*out = new orc_tape{simplify(*t->t, choices, n, t->t->d.n_regs)});
 }
+// VmData::simplify::<M> with a different register count (vm/data.rs:411-437)
+int32_t orc_simplify_n(const orc_tape* t, const uint8_t* choices, size_t n, uint32_t n_regs, orc_tape** out) {
+    ORC_TRY(*out = new orc_tape{simplify(*t->t, choices, n, n_regs)});
+}
 // Bytecode of an oracle tape (e.g. a simplified child), for feeding the GPU path
 int32_t orc_tape_bytecode(const orc_tape* t, int32_t repack, uint32_t* words, size_t cap, size_t* n_words,
                           uint8_t* reg_count, uint32_t* mem_count) {

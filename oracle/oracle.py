@@ -45,6 +45,7 @@ def lib() -> C.CDLL:
     L.orc_float_slice_eval.argtypes = [vp, P(fp), P(fp), C.c_uint64]
     L.orc_grad_slice_eval.argtypes = [vp, P(fp), P(fp), C.c_uint64]
     L.orc_simplify.argtypes = [vp, P(C.c_uint8), C.c_size_t, P(vp)]
+    L.orc_simplify_n.argtypes = [vp, P(C.c_uint8), C.c_size_t, u32, P(vp)]
     L.orc_tape_bytecode.argtypes = [vp, i32, P(u32), C.c_size_t, P(C.c_size_t), P(C.c_uint8), P(u32)]
     L.orc_screen_to_world_2d.argtypes = [u32, u32, fp]
     L.orc_screen_to_world_2d.restype = None
@@ -167,10 +168,14 @@ class Tape:
         _ck(lib().orc_grad_slice_eval(self._h, arr, oarr, n))
         return out
 
-    def simplify(self, choices):
+    def simplify(self, choices, n_regs=None):
         c = np.ascontiguousarray(choices, dtype=np.uint8)
         h = C.c_void_p()
-        _ck(lib().orc_simplify(self._h, c.ctypes.data_as(C.POINTER(C.c_uint8)), len(c), C.byref(h)))
+        cp = c.ctypes.data_as(C.POINTER(C.c_uint8))
+        if n_regs is None:
+            _ck(lib().orc_simplify(self._h, cp, len(c), C.byref(h)))
+        else:
+            _ck(lib().orc_simplify_n(self._h, cp, len(c), n_regs, C.byref(h)))
         return Tape(h)
 
     def bytecode(self, repack=True):
