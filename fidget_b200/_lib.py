@@ -63,6 +63,7 @@ class FcRenderStats(C.Structure):
 
 FC_FLAG_ASYNC = 1
 FC_FLAG_TIMING = 2
+FC_FLAG_NO_CLAMP = 4
 
 # name -> (restype, argtypes); mirrors include/fidget_cuda.h one to one
 _vp, _u32, _i32, _u64, _u8 = C.c_void_p, C.c_uint32, C.c_int32, C.c_uint64, C.c_uint8

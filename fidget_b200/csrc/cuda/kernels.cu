@@ -203,8 +203,10 @@ __device__ __forceinline__ void simplify_lane(const uint2* __restrict__ tape, ui
     auto clear = [&](uint32_t r) { live[r >> 5][lane] &= ~(1u << (r & 31u)); };
     uint2* wp = wend;
     uint32_t ref = 0, nch = 0;
+    uint2 nxt = n_ops ? __ldg(tape + (n_ops - 1)) : make_uint2(0, 0);
     for (int i = int(n_ops) - 1; i >= 0; --i) {
-        uint2 w = __ldg(tape + i);
+        const uint2 w = nxt;
+        if (i > 0) nxt = __ldg(tape + (i - 1));   // prefetch: the clause stream is the latency chain here
         Dec d(w.x);
         uint32_t c = 3u;
         bool is_choice = op_is_choice(d.op);
@@ -262,9 +264,13 @@ __device__ __forceinline__ void simplify_lane(const uint2* __restrict__ tape, ui
 }
 
 // ---------------------------------------------------------------------------
-// K1: interval level kernel (2D)
+// K1: interval level kernel.  DIM = 2: pixel::render tiles (fill records are
+// painted later by k_fill_2d).  DIM = 3: voxel::render tiles; an
+// interval-proven-inside tile raises the heightmap to its top + 1
+// (voxel.rs:310-317), heightmap entries are (depth << 32 | leaf job id + 1).
+template <int DIM>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-k_interval_level_2d(const __grid_constant__ LevelParams p) {
+k_interval_level(const __grid_constant__ LevelParams p) {
     __shared__ uint32_t live_s[WARPS_PER_BLOCK][8][32];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -272,8 +278,8 @@ k_interval_level_2d(const __grid_constant__ LevelParams p) {
     uint32_t* cs = p.choice_scratch + size_t(gw) * p.choice_words * 32u + lane;
     itv slots[REG_SLOTS];
 
-    const uint32_t n_roots = p.roots_x * p.roots_y;
-    const uint32_t n_jobs = p.root_mode ? (n_roots + 31u) / 32u : p.ctr->n_jobs[p.level];
+    const uint32_t n_roots = p.roots_x * p.roots_y * (DIM == 3 ? p.roots_z : 1u);
+    const uint32_t n_jobs = p.root_mode ? (n_roots + 31u) / 32u : min(p.ctr->n_jobs[p.level], p.cap_in);
     const uint32_t T = p.tile;
 
     for (;;) {
@@ -283,7 +289,7 @@ k_interval_level_2d(const __grid_constant__ LevelParams p) {
         if (j >= n_jobs) break;
 
         TapeRef tr;
-        uint32_t px = 0, py = 0, nchild;
+        uint32_t px = 0, py = 0, pz = 0, nchild;
         if (p.root_mode) {
             tr = p.root_tape;
             nchild = min(32u, n_roots - j * 32u);
@@ -291,28 +297,31 @@ k_interval_level_2d(const __grid_constant__ LevelParams p) {
             const TileJob* job = p.jobs_in + j;
             px = job->x;
             py = job->y;
+            pz = job->z;
             tr = job->tape;
-            nchild = p.n_axis * p.n_axis;
+            nchild = p.n_axis * p.n_axis * (DIM == 3 ? p.n_axis : 1u);
         }
         const uint2* tape = tr.ptr;
 
         for (uint32_t chunk = 0; chunk * 32u < nchild; ++chunk) {
             const uint32_t c = chunk * 32u + lane;
             const bool valid = c < nchild;
-            uint32_t cx, cy;
+            uint32_t cx, cy, cz = 0;
             if (p.root_mode) {
                 uint32_t idx = j * 32u + (valid ? c : 0u);
                 cx = p.root_x0 + (idx % p.roots_x) * T;
-                cy = p.root_y0 + (idx / p.roots_x) * T;
+                cy = p.root_y0 + ((idx / p.roots_x) % p.roots_y) * T;
+                if (DIM == 3) cz = p.root_z0 + (idx / (p.roots_x * p.roots_y)) * T;
             } else {
                 uint32_t cc = valid ? c : 0u;
                 cx = px + (cc % p.n_axis) * T;
-                cy = py + (cc / p.n_axis) * T;
+                cy = py + ((cc / p.n_axis) % p.n_axis) * T;
+                if (DIM == 3) cz = pz + (cc / (p.n_axis * p.n_axis)) * T;
             }
-            // Region in screen coordinates -> model space (pixel.rs:325-342)
+            // Region in screen coordinates -> model space (pixel.rs:325-342, voxel.rs:291-306)
             itv X = iv(float(cx), float(cx) + float(T));
             itv Y = iv(float(cy), float(cy) + float(T));
-            itv Z = iv(p.z2d, p.z2d);
+            itv Z = DIM == 3 ? iv(float(cz), float(cz) + float(T)) : iv(p.z2d, p.z2d);
             itv vx, vy, vz;
             xform_iv(p.mat, X, Y, Z, vx, vy, vz);
 
@@ -330,8 +339,31 @@ k_interval_level_2d(const __grid_constant__ LevelParams p) {
             const bool fill_out = valid && !p.pixel_perfect && !fill_in && r.x > 0.0f;
             const bool amb = valid && !fill_in && !fill_out;
 
-            // fills
-            {
+            if (DIM == 3) {
+                // full tile: depth = max(depth, top + 1) over its footprint (voxel.rs:310-317)
+                uint32_t m = __ballot_sync(FULL, fill_in);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t fx = __shfl_sync(FULL, cx, src), fy = __shfl_sync(FULL, cy, src),
+                                   fz = __shfl_sync(FULL, cz, src);
+                    const unsigned long long key = (unsigned long long)(fz + T + 1u) << 32;
+                    for (uint32_t q = lane; q < T * T; q += 32u) {
+                        const uint32_t x = fx + q % T, y = fy + q / T;
+                        if (x < p.width && y < p.height) atomicMax(&p.heightmap[size_t(y) * p.width + x], key);
+                    }
+                }
+                if (p.stats) {
+                    uint32_t mv = __ballot_sync(FULL, valid), mi = __ballot_sync(FULL, fill_in),
+                             mo = __ballot_sync(FULL, fill_out), ma = __ballot_sync(FULL, amb);
+                    if (lane == 0) {
+                        atomicAdd(&p.stats->evaluated[p.level], (unsigned long long)__popc(mv));
+                        if (mi) atomicAdd(&p.stats->filled_inside[p.level], (unsigned long long)__popc(mi));
+                        if (mo) atomicAdd(&p.stats->filled_outside[p.level], (unsigned long long)__popc(mo));
+                        if (ma) atomicAdd(&p.stats->ambiguous[p.level], (unsigned long long)__popc(ma));
+                    }
+                }
+            } else {
                 uint32_t m = __ballot_sync(FULL, fill_in || fill_out);
                 if (m) {
                     uint32_t base = 0;
@@ -407,7 +439,7 @@ k_interval_level_2d(const __grid_constant__ LevelParams p) {
                         TileJob o;
                         o.x = cx;
                         o.y = cy;
-                        o.z = 0;
+                        o.z = cz;
                         o.pad = 0;
                         o.tape = child;
                         p.jobs_out[slot] = o;
@@ -421,7 +453,169 @@ k_interval_level_2d(const __grid_constant__ LevelParams p) {
 }
 
 void launch_interval_level_2d(const LevelParams& p, int blocks, cudaStream_t s) {
-    k_interval_level_2d<<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(p);
+    k_interval_level<2><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(p);
+}
+void launch_interval_level_3d(const LevelParams& p, int blocks, cudaStream_t s) {
+    k_interval_level<3><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(p);
+}
+
+// ---------------------------------------------------------------------------
+// K2 (3D): leaf voxels.  One warp per leaf tile; each lane owns two XY columns
+// and walks Z front to back (k descending), two points per tape pass; the
+// warp stops as soon as every column has hit the surface (voxel.rs:359-447).
+__global__ void __launch_bounds__(128) k_voxels_3d(const __grid_constant__ VoxelParams p) {
+    const int lane = threadIdx.x & 31;
+    float2 slots[REG_SLOTS];
+    const uint32_t n_jobs = min(p.ctr->n_jobs[p.list], p.cap_jobs);
+    const uint32_t T = p.tile, ncol = T * T;
+    unsigned long long shaded = 0;
+    for (;;) {
+        uint32_t j = 0;
+        if (lane == 0) j = atomicAdd(&p.ctr->cursor[p.cursor], 1u);
+        j = __shfl_sync(FULL, j, 0);
+        if (j >= n_jobs) break;
+        const TileJob* job = p.jobs + j;
+        const uint32_t cx = job->x, cy = job->y, cz = job->z;
+        const TapeRef tr = job->tape;
+        const uint2* tape = tr.ptr;
+        const unsigned long long id = (unsigned long long)(j + 1u);
+        for (uint32_t base = 0; base < ncol; base += 64u) {
+            const uint32_t c0 = base + lane, c1 = c0 + 32u;
+            const bool v0 = c0 < ncol, v1 = c1 < ncol;
+            const uint32_t i0 = (v0 ? c0 : 0u) % T, j0 = (v0 ? c0 : 0u) / T;
+            const uint32_t i1 = (v1 ? c1 : 0u) % T, j1 = (v1 ? c1 : 0u) / T;
+            const uint32_t gx0 = cx + i0, gy0 = cy + j0, gx1 = cx + i1, gy1 = cy + j1;
+            const bool in0 = v0 && gx0 < p.width && gy0 < p.height, in1 = v1 && gx1 < p.width && gy1 < p.height;
+            // columns already at or above this tile's top are skipped (voxel.rs:376-381)
+            const uint32_t zmax = cz + T;
+            bool done0 = !in0 || uint32_t(p.heightmap[size_t(gy0) * p.width + gx0] >> 32) >= zmax;
+            bool done1 = !in1 || uint32_t(p.heightmap[size_t(gy1) * p.width + gx1] >> 32) >= zmax;
+            for (int k = int(T) - 1; k >= 0; --k) {
+                if (__all_sync(FULL, done0 && done1)) break;
+                float x0, y0, z0, x1, y1, z1;
+                xform_f32(p.mat, float(gx0), float(gy0), float(cz + uint32_t(k)), x0, y0, z0);
+                xform_f32(p.mat, float(gx1), float(gy1), float(cz + uint32_t(k)), x1, y1, z1);
+                const float2 X = make_float2(x0, x1), Y = make_float2(y0, y1), Z = make_float2(z0, z1);
+                const int ix = p.var_x, iy = p.var_y;
+                const float2 r = run_f32x2(tape, tr.n_ops, slots,
+                                           [&](uint32_t i) { return int(i) == ix ? X : (int(i) == iy ? Y : Z); });
+                const unsigned long long key = ((unsigned long long)(cz + uint32_t(k) + 1u) << 32) | id;
+                if (!done0) {
+                    ++shaded;
+                    if (r.x < 0.0f) { atomicMax(&p.heightmap[size_t(gy0) * p.width + gx0], key); done0 = true; }
+                }
+                if (!done1) {
+                    ++shaded;
+                    if (r.y < 0.0f) { atomicMax(&p.heightmap[size_t(gy1) * p.width + gx1], key); done1 = true; }
+                }
+            }
+        }
+    }
+    if (p.stats) {
+        for (int o = 16; o > 0; o >>= 1) shaded += __shfl_xor_sync(FULL, shaded, o);
+        if (lane == 0 && shaded) atomicAdd(&p.stats->pixels, shaded);
+    }
+}
+void launch_voxels_3d(const VoxelParams& p, int blocks, cudaStream_t s) { k_voxels_3d<<<blocks, 128, 0, s>>>(p); }
+
+// Gradient interpreter (VmGradSliceEval, vm/mod.rs:1097-1396)
+template <class Input>
+__device__ __forceinline__ grd run_grad(const uint2* __restrict__ tape, uint32_t n_ops, grd* slots, Input input) {
+    grd result = gr1(nanf_());
+    for (uint32_t i = 0; i < n_ops; ++i) {
+        const uint2 w = __ldg(tape + i);
+        Dec d(w.x);
+        const float imm = __uint_as_float(w.y);
+        const grd sl = slots[d.lhs], sr = slots[d.rhs];
+        const grd a = d.form == F_IR ? gr1(imm) : sl;
+        const grd b = d.form == F_RI ? gr1(imm) : sr;
+        grd r;
+        if (d.op == OP_MEM) {
+            if (d.form == F_RI) slots[d.out] = slots[MEM_BASE + w.y];
+            else slots[MEM_BASE + w.y] = sl;
+            continue;
+        } else if (d.op >= OP_ADD) {
+            if (d.op == OP_MUL && d.form == F_RI) r = gr_mul_f(sl, imm);
+            else r = gr_binary(d.op, a, b);
+        } else if (d.op >= OP_NEG) r = gr_unary(d.op, sl);
+        else if (d.op == OP_COPY) r = d.form == F_RI ? gr1(imm) : sl;
+        else if (d.op == OP_INPUT) r = input(w.y);
+        else { if (w.y == 0) result = sl; continue; }
+        slots[d.out] = r;
+    }
+    return result;
+}
+
+// K3: normals + final image.  One thread per pixel; the gradient is evaluated
+// at the surface voxel (x, y, depth - 1) with the tape of the
+// leaf tile that found it (voxel.rs:449-481); lanes of a warp that share a
+// leaf tile run its tape together.
+__global__ void __launch_bounds__(128) k_normals_3d(const __grid_constant__ NormalParams p) {
+    grd slots[REG_SLOTS];
+    const int lane = threadIdx.x & 31;
+    // 8x4 pixel patch per warp
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t patches_x = (p.width + 7u) / 8u, patches_y = (p.height + 3u) / 4u;
+    if (warp >= patches_x * patches_y) return;
+    const uint32_t x = (warp % patches_x) * 8u + (lane & 7), y = (warp / patches_x) * 4u + (lane >> 3);
+    const bool inb = x < p.width && y < p.height;
+    const unsigned long long key = inb ? p.heightmap[size_t(y) * p.width + x] : 0ull;
+    const uint32_t depth = uint32_t(key >> 32), id = uint32_t(key);
+    grd g = gr(0.0f, 0.0f, 0.0f, 0.0f);
+    bool pending = inb && id != 0u;
+    unsigned long long n = 0;
+    for (;;) {
+        const uint32_t m = __ballot_sync(FULL, pending);
+        if (!m) break;
+        const uint32_t lead_id = __shfl_sync(FULL, id, __ffs(m) - 1);
+        const bool mine = pending && id == lead_id;
+        const TileJob* job = p.jobs + (lead_id - 1u);
+        const TapeRef tr = job->tape;
+        grd gx, gy, gz;
+        xform_gr(p.mat, gr(float(x), 1.0f, 0.0f, 0.0f), gr(float(y), 0.0f, 1.0f, 0.0f),
+                 gr(float(depth - 1u), 0.0f, 0.0f, 1.0f), gx, gy, gz);
+        const int ix = p.var_x, iy = p.var_y;
+        const grd r = run_grad(tr.ptr, tr.n_ops, slots,
+                               [&](uint32_t i) { return int(i) == ix ? gx : (int(i) == iy ? gy : gz); });
+        if (mine) { g = r; pending = false; ++n; }
+    }
+    if (inb) {
+        float4 o;
+        if (p.clamp && depth >= p.depth - 1u) {   // voxel.rs:535-546
+            o = make_float4(0.0f, 0.0f, 1.0f, __uint_as_float(p.depth));
+        } else {
+            o = make_float4(g.y, g.z, g.w, __uint_as_float(depth));
+        }
+        reinterpret_cast<float4*>(p.out)[size_t(y) * p.width + x] = o;
+    }
+    if (p.stats) {
+        for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(FULL, n, o);
+        if (lane == 0 && n) atomicAdd(&p.stats->grads, n);
+    }
+}
+void launch_normals_3d(const NormalParams& p, cudaStream_t s) {
+    const uint64_t warps = uint64_t((p.width + 7u) / 8u) * ((p.height + 3u) / 4u);
+    k_normals_3d<<<unsigned((warps + 3) / 4), 128, 0, s>>>(p);
+}
+
+// Multi-GPU: per-pixel merge of Z-ordered slab images; the highest slab with
+// the greatest depth wins, then the final clamp is applied.
+__global__ void k_merge_slabs(const float4* const* slabs, uint32_t n_slabs, uint32_t n_pixels, uint32_t depth,
+                              float4* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pixels) return;
+    float4 best = slabs[0][i];
+    for (uint32_t s = 1; s < n_slabs; ++s) {
+        const float4 c = slabs[s][i];
+        if (__float_as_uint(c.w) >= __float_as_uint(best.w)) best = c;
+    }
+    if (__float_as_uint(best.w) >= depth - 1u) best = make_float4(0.0f, 0.0f, 1.0f, __uint_as_float(depth));
+    out[i] = best;
+}
+void launch_merge_slabs(const void* const* d_slabs, uint32_t n_slabs, uint32_t n_pixels, uint32_t depth, void* out,
+                        cudaStream_t s) {
+    k_merge_slabs<<<(n_pixels + 255) / 256, 256, 0, s>>>(reinterpret_cast<const float4* const*>(d_slabs), n_slabs,
+                                                         n_pixels, depth, reinterpret_cast<float4*>(out));
 }
 
 // ---------------------------------------------------------------------------
@@ -773,13 +967,34 @@ k_interval_root_coop_2d(const __grid_constant__ LevelParams p) {
         auto ld = [&](uint32_t id) { return id != COOP_NONE ? vals[id] : iv_nan(); };
 
         // ---- forward: dependency waves ----
-        for (uint32_t w = 0; w < p.sched.n_waves; ++w) {
-            const uint32_t e = ws[w + 1];
-            for (uint32_t i = ws[w] + tid; i < e; i += COOP_THREADS) {
-                const Rec rc = load_rec(recs, i);
-                vals[rc.p] = exec(rc, ld(rc.ia), ld(rc.ib));
+        {
+            // each thread keeps the NEXT record it will execute in registers, so the
+            // global (L2) latency of the schedule stream overlaps the current clause
+            uint32_t w = 0, i = tid;   // recs of wave w are [ws[w], ws[w+1]); wave 0 starts at 0
+            const uint32_t n_waves = p.sched.n_waves, wave_end_all = p.sched.tail_begin;
+            uint32_t e = n_waves ? ws[1] : 0;
+            auto advance = [&]() {     // move (w, i) to this thread's next record, crossing waves
+                while (w < n_waves && i >= e) {
+                    ++w;
+                    if (w < n_waves) { i = e + tid; e = ws[w + 1]; }
+                }
+            };
+            advance();
+            uint4 q = (w < n_waves) ? __ldg(reinterpret_cast<const uint4*>(recs) + i) : make_uint4(0, 0, 0, 0);
+            uint32_t cur_w = 0;
+            while (cur_w < n_waves) {
+                // run everything this thread owns in wave cur_w
+                while (w == cur_w) {
+                    const Rec rc(q);
+                    i += COOP_THREADS;
+                    advance();
+                    if (w < n_waves) q = __ldg(reinterpret_cast<const uint4*>(recs) + i);
+                    vals[rc.p] = exec(rc, ld(rc.ia), ld(rc.ib));
+                }
+                __syncthreads();
+                ++cur_w;
             }
-            __syncthreads();
+            (void)wave_end_all;
         }
         // ---- forward: tail segments ----
         for (uint32_t sgi = 0; sgi < p.sched.n_segs; ++sgi) {

@@ -55,7 +55,7 @@ struct Counters {
 // tape in SSA form (value id = position of the defining clause), clauses
 // grouped into dependency waves; a trailing run of single-clause waves is the
 // serial tail.
-constexpr int COOP_THREADS = 128;
+constexpr int COOP_THREADS = 256;
 constexpr uint32_t COOP_NONE = 0xFFFFu;
 struct CoopRec {
     uint32_t x, y;        // the device clause
@@ -97,6 +97,7 @@ struct LevelParams {
     Mat4 mat;
     // lists
     const TileJob* jobs_in;
+    uint32_t cap_in;
     TileJob* jobs_out;
     uint32_t cap_out;
     FillRec* fills;
@@ -110,7 +111,7 @@ struct LevelParams {
     Counters* ctr;
     Stats* stats;
     // 3D
-    uint32_t* heightmap;            // width*height depth values (atomicMax)
+    unsigned long long* heightmap;  // 3D: width*height keys (depth << 32 | leaf job id + 1), atomicMax
     uint32_t n_vars;
     int var_x, var_y, var_z;
 };
@@ -136,7 +137,34 @@ struct FillParams {
     float* out;
 };
 
+struct VoxelParams {
+    uint32_t tile, width, height;
+    Mat4 mat;
+    const TileJob* jobs;
+    uint32_t cap_jobs;
+    unsigned long long* heightmap;
+    Counters* ctr;
+    int list, cursor;
+    Stats* stats;
+    int var_x, var_y, var_z;
+};
+struct NormalParams {
+    uint32_t width, height, depth;
+    uint32_t clamp;             // apply the final `depth >= D-1` clamp (voxel.rs:535-546)
+    Mat4 mat;
+    const TileJob* jobs;        // leaf jobs
+    const unsigned long long* heightmap;
+    void* out;                  // GeometryPixel[width*height]
+    Stats* stats;
+    int var_x, var_y, var_z;
+};
+
 // launchers (kernels.cu)
+void launch_interval_level_3d(const LevelParams& p, int blocks, cudaStream_t s);
+void launch_voxels_3d(const VoxelParams& p, int blocks, cudaStream_t s);
+void launch_normals_3d(const NormalParams& p, cudaStream_t s);
+void launch_merge_slabs(const void* const* d_slabs, uint32_t n_slabs, uint32_t n_pixels, uint32_t depth, void* out,
+                        cudaStream_t s);
 void launch_interval_level_2d(const LevelParams& p, int blocks, cudaStream_t s);
 size_t coop_smem_bytes(uint32_t n_ops, uint32_t n_choices);
 cudaError_t launch_interval_root_coop_2d(const LevelParams& p, int blocks, cudaStream_t s);

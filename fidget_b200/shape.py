@@ -299,6 +299,7 @@ class RenderConfig3D:
     mat: np.ndarray | None = None
     z_range: tuple = (0, 0)
     timing: bool = False
+    clamp: bool = True                          # False for slab renders (fc_merge_slabs applies it)
 
     def matrix(self):
         return self.mat if self.mat is not None else voxel_mat(self.width, self.height, self.depth,
@@ -335,7 +336,8 @@ def render3d(shape: CudaShape, cfg: RenderConfig3D, out=None, stats: bool = Fals
     c.n_tile_sizes = len(cfg.tile_sizes)
     for i, t in enumerate(cfg.tile_sizes):
         c.tile_sizes[i] = t
-    c.flags = (_lib.FC_FLAG_TIMING if cfg.timing else 0) | (_lib.FC_FLAG_ASYNC if asynchronous else 0)
+    c.flags = (_lib.FC_FLAG_TIMING if cfg.timing else 0) | (_lib.FC_FLAG_ASYNC if asynchronous else 0) | \
+        (0 if cfg.clamp else _lib.FC_FLAG_NO_CLAMP)
     c.z_begin, c.z_end = cfg.z_range
     if out is None:
         out = np.zeros((cfg.height, cfg.width), dtype=GEOMETRY_PIXEL)

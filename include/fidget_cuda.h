@@ -134,6 +134,7 @@ int32_t fc_simplify(fc_eval* e, const fc_tape* parent, const uint8_t* choices, s
 #define FC_MAX_TILE_LEVELS 8
 #define FC_FLAG_ASYNC 1u        /* enqueue only; errors surface in fc_ctx_synchronize */
 #define FC_FLAG_TIMING 2u       /* record per-stage CUDA events (fc_render_stats.stage_ms) */
+#define FC_FLAG_NO_CLAMP 4u     /* fc_render3d: skip the final depth clamp (slab renders; fc_merge_slabs applies it) */
 
 typedef struct fc_render2d_cfg {
     uint32_t width, height;

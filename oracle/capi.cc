@@ -122,13 +122,14 @@ void orc_transform_f32(const float* m16, float x, float y, float z, float* out3)
 
 int32_t orc_render2d(const orc_tape* t, uint32_t w, uint32_t h, const float* mat16, float z, int32_t pixel_perfect,
                      const uint32_t* tile_sizes, uint32_t n_tile_sizes, int32_t threads, uint32_t first_root,
-                     uint32_t n_roots, float* out, orc_stats* stats) {
+                     uint32_t n_roots, const float* var_values, uint32_t n_var_values, float* out, orc_stats* stats) {
     ORC_TRY({
         Render2DConfig cfg;
         cfg.width = w; cfg.height = h; cfg.mat = to_mat(mat16); cfg.z = z;
         cfg.pixel_perfect = pixel_perfect != 0;
         if (n_tile_sizes) cfg.tile_sizes.assign(tile_sizes, tile_sizes + n_tile_sizes);
         cfg.threads = threads; cfg.first_root = first_root; cfg.n_roots = n_roots;
+        if (n_var_values) cfg.var_values.assign(var_values, var_values + n_var_values);
         TileStats s;
         render2d(t->t, cfg, out, &s);
         copy_stats(s, stats);
@@ -136,12 +137,13 @@ int32_t orc_render2d(const orc_tape* t, uint32_t w, uint32_t h, const float* mat
 }
 int32_t orc_render3d(const orc_tape* t, uint32_t w, uint32_t h, uint32_t d, const float* mat16,
                      const uint32_t* tile_sizes, uint32_t n_tile_sizes, int32_t threads, uint32_t first_root,
-                     uint32_t n_roots, void* out, orc_stats* stats) {
+                     uint32_t n_roots, const float* var_values, uint32_t n_var_values, void* out, orc_stats* stats) {
     ORC_TRY({
         Render3DConfig cfg;
         cfg.width = w; cfg.height = h; cfg.depth = d; cfg.mat = to_mat(mat16);
         if (n_tile_sizes) cfg.tile_sizes.assign(tile_sizes, tile_sizes + n_tile_sizes);
         cfg.threads = threads; cfg.first_root = first_root; cfg.n_roots = n_roots;
+        if (n_var_values) cfg.var_values.assign(var_values, var_values + n_var_values);
         TileStats s;
         render3d(t->t, cfg, reinterpret_cast<GeometryPixel*>(out), &s);
         copy_stats(s, stats);

@@ -57,8 +57,8 @@ def lib() -> C.CDLL:
     L.orc_mat4_mul.restype = None
     L.orc_transform_f32.argtypes = [fp, C.c_float, C.c_float, C.c_float, fp]
     L.orc_transform_f32.restype = None
-    L.orc_render2d.argtypes = [vp, u32, u32, fp, C.c_float, i32, P(u32), u32, i32, u32, u32, fp, vp]
-    L.orc_render3d.argtypes = [vp, u32, u32, u32, fp, P(u32), u32, i32, u32, u32, vp, vp]
+    L.orc_render2d.argtypes = [vp, u32, u32, fp, C.c_float, i32, P(u32), u32, i32, u32, u32, fp, u32, fp, vp]
+    L.orc_render3d.argtypes = [vp, u32, u32, u32, fp, P(u32), u32, i32, u32, u32, fp, u32, vp, vp]
     _LIB = L
     return L
 
@@ -221,27 +221,29 @@ def voxel_mat(w, h, d, world_to_model=None):
 
 
 def render2d(tape: Tape, width, height, mat=None, z=0.0, pixel_perfect=False, tile_sizes=(128, 32, 8),
-             threads=1, first_root=0, n_roots=0):
+             threads=1, first_root=0, n_roots=0, var_values=None):
     """Returns (image float32 [h,w] holding RawDistancePixel bits, stats dict)."""
     mat = pixel_mat(width, height) if mat is None else mat
     m = np.ascontiguousarray(mat, dtype=np.float32).reshape(16)
     ts = (C.c_uint32 * len(tile_sizes))(*tile_sizes)
     out = np.zeros((height, width), dtype=np.float32)
     st = OrcStats()
+    vv = np.ascontiguousarray(var_values if var_values is not None else [], dtype=np.float32)
     _ck(lib().orc_render2d(tape._h, width, height, _fp(m), z, int(pixel_perfect), ts, len(tile_sizes),
-                           threads, first_root, n_roots, _fp(out), C.byref(st)))
+                           threads, first_root, n_roots, _fp(vv), len(vv), _fp(out), C.byref(st)))
     return out, st.as_dict()
 
 
 def render3d(tape: Tape, width, height, depth, mat=None, tile_sizes=(128, 64, 32, 16, 8), threads=1,
-             first_root=0, n_roots=0):
+             first_root=0, n_roots=0, var_values=None):
     mat = voxel_mat(width, height, depth) if mat is None else mat
     m = np.ascontiguousarray(mat, dtype=np.float32).reshape(16)
     ts = (C.c_uint32 * len(tile_sizes))(*tile_sizes)
     out = np.zeros((height, width), dtype=GEOMETRY_PIXEL)
     st = OrcStats()
+    vv = np.ascontiguousarray(var_values if var_values is not None else [], dtype=np.float32)
     _ck(lib().orc_render3d(tape._h, width, height, depth, _fp(m), ts, len(tile_sizes), threads,
-                           first_root, n_roots, out.ctypes.data_as(C.c_void_p), C.byref(st)))
+                           first_root, n_roots, _fp(vv), len(vv), out.ctypes.data_as(C.c_void_p), C.byref(st)))
     return out, st.as_dict()
 
 

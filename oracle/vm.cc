@@ -517,9 +517,20 @@ VarSlots var_slots(const Tape& t) {
         if (v.kind == Var::X) s.x = int(i);
         else if (v.kind == Var::Y) s.y = int(i);
         else if (v.kind == Var::Z) s.z = int(i);
-        else throw std::runtime_error("oracle renderers only support X/Y/Z variables");
     }
     return s;
+}
+
+// Scratch for tracing / bulk inputs: every slot gets its bound value, then
+// the axes overwrite theirs (ShapeTracingEval::eval_raw, shape/mod.rs:520-533)
+template <class T>
+void bind_vars(const Tape& t, const std::vector<float>& values, std::vector<T>& out) {
+    out.assign(std::max<size_t>(t.n_vars(), 3), T(0.0f));
+    for (size_t i = 0; i < t.n_vars(); ++i) {
+        if (t.d.vars.order[i].kind != Var::V) continue;
+        if (i >= values.size()) throw std::runtime_error("missing value for a bound variable");
+        out[i] = T(values[i]);
+    }
 }
 
 void add_stats(TileStats& a, const TileStats& b) {
@@ -553,6 +564,18 @@ namespace {
 struct Worker2D {
     const Render2DConfig& cfg;
     std::vector<uint32_t> ts;
+    std::vector<Interval> ivars;
+    std::vector<std::vector<float>> fconst;
+    std::vector<const float*> bulk_vars(const Tape& t, size_t n) {
+        std::vector<const float*> v(std::max<size_t>(t.n_vars(), 3), sx.data());
+        fconst.resize(t.n_vars());
+        for (size_t q = 0; q < t.n_vars(); ++q)
+            if (t.d.vars.order[q].kind == Var::V) {
+                fconst[q].assign(n, cfg.var_values.at(q));
+                v[q] = fconst[q].data();
+            }
+        return v;
+    }
     IntervalEval ieval;
     FloatSliceEval feval;
     std::vector<float> sx, sy, sz, sout;
@@ -574,7 +597,8 @@ struct Worker2D {
         Interval xyz[3];
         transform_interval(x, y, z, cfg.mat, xyz);
         VarSlots vs = var_slots(tape);
-        Interval vars[3];
+        bind_vars(tape, cfg.var_values, ivars);
+        Interval* vars = ivars.data();
         if (vs.x >= 0) vars[vs.x] = xyz[0];
         if (vs.y >= 0) vars[vs.y] = xyz[1];
         if (vs.z >= 0) vars[vs.z] = xyz[2];
@@ -622,12 +646,12 @@ struct Worker2D {
                 ++index;
             }
         VarSlots vs = var_slots(tape);
-        const float* vars[3] = {sx.data(), sx.data(), sx.data()};
+        std::vector<const float*> vars = bulk_vars(tape, n);
         if (vs.x >= 0) vars[vs.x] = sx.data();
         if (vs.y >= 0) vars[vs.y] = sy.data();
         if (vs.z >= 0) vars[vs.z] = sz.data();
         float* outs[1] = {sout.data()};
-        feval.eval(tape, vars, n, outs);
+        feval.eval(tape, vars.data(), n, outs);
         stats.pixels += n;
         index = 0;
         for (uint32_t j = 0; j < tile_size; ++j) {
@@ -682,6 +706,18 @@ namespace {
 struct Worker3D {
     const Render3DConfig& cfg;
     std::vector<uint32_t> ts;
+    std::vector<Interval> ivars;
+    std::vector<std::vector<float>> fconst;
+    std::vector<const float*> bulk_vars(const Tape& t, size_t n) {
+        std::vector<const float*> v(std::max<size_t>(t.n_vars(), 3), sx.data());
+        fconst.resize(t.n_vars());
+        for (size_t q = 0; q < t.n_vars(); ++q)
+            if (t.d.vars.order[q].kind == Var::V) {
+                fconst[q].assign(n, cfg.var_values.at(q));
+                v[q] = fconst[q].data();
+            }
+        return v;
+    }
     IntervalEval ieval;
     FloatSliceEval feval;
     GradSliceEval geval;
@@ -717,7 +753,8 @@ struct Worker3D {
         Interval xyz[3];
         transform_interval(x, y, z, cfg.mat, xyz);
         VarSlots vs = var_slots(tape);
-        Interval vars[3];
+        bind_vars(tape, cfg.var_values, ivars);
+        Interval* vars = ivars.data();
         if (vs.x >= 0) vars[vs.x] = xyz[0];
         if (vs.y >= 0) vars[vs.y] = xyz[1];
         if (vs.z >= 0) vars[vs.z] = xyz[2];
@@ -775,12 +812,12 @@ struct Worker3D {
         size_t size = index;
         if (size == 0) return;  // (the reference asserts size > 0; unreachable after the early-out)
         VarSlots vs = var_slots(tape);
-        const float* vars[3] = {sx.data(), sx.data(), sx.data()};
+        std::vector<const float*> vars = bulk_vars(tape, size);
         if (vs.x >= 0) vars[vs.x] = sx.data();
         if (vs.y >= 0) vars[vs.y] = sy.data();
         if (vs.z >= 0) vars[vs.z] = sz.data();
         float* outs[1] = {sout.data()};
-        feval.eval(tape, vars, size, outs);
+        feval.eval(tape, vars.data(), size, outs);
         stats.pixels += size;
 
         size_t grad = 0;
@@ -809,12 +846,18 @@ struct Worker3D {
                 transform_grad(gx[q], gy[q], gz[q], cfg.mat, t);
                 gx[q] = t[0]; gy[q] = t[1]; gz[q] = t[2];
             }
-            const Grad* gvars[3] = {gx.data(), gx.data(), gx.data()};
+            std::vector<std::vector<Grad>> gconst(tape.n_vars());
+            std::vector<const Grad*> gvars(std::max<size_t>(tape.n_vars(), 3), gx.data());
+            for (size_t q = 0; q < tape.n_vars(); ++q)
+                if (tape.d.vars.order[q].kind == Var::V) {
+                    gconst[q].assign(grad, Grad(cfg.var_values.at(q)));
+                    gvars[q] = gconst[q].data();
+                }
             if (vs.x >= 0) gvars[vs.x] = gx.data();
             if (vs.y >= 0) gvars[vs.y] = gy.data();
             if (vs.z >= 0) gvars[vs.z] = gz.data();
             Grad* gouts[1] = {gout.data()};
-            geval.eval(tape, gvars, grad, gouts);
+            geval.eval(tape, gvars.data(), grad, gouts);
             for (size_t q = 0; q < grad; ++q) {
                 GeometryPixel& p = out[columns[q]];
                 p.normal[0] = gout[q].dx; p.normal[1] = gout[q].dy; p.normal[2] = gout[q].dz;

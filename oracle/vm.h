@@ -99,6 +99,8 @@ struct Render2DConfig {
     bool pixel_perfect = false;
     std::vector<uint32_t> tile_sizes = {128, 32, 8};
     int threads = 1;
+    // values for non-XYZ variables, indexed by tape input slot (ShapeVars, shape/mod.rs:548-640)
+    std::vector<float> var_values;
     // restrict to root tiles [first, first+count) in the reference's
     // enumeration order (x-major); count = 0 means all
     uint32_t first_root = 0, n_roots = 0;
@@ -112,6 +114,7 @@ struct Render3DConfig {
     Mat4 mat;
     std::vector<uint32_t> tile_sizes = {128, 64, 32, 16, 8};
     int threads = 1;
+    std::vector<float> var_values;
     uint32_t first_root = 0, n_roots = 0;
     // Z range restriction [z_begin, z_end) in voxels for slab sharding tests;
     // z_end = 0 means full depth.  Root tiles outside the slab are skipped.

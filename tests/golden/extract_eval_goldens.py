@@ -72,6 +72,15 @@ def parse_tests(path, prefix):
         body = src[start:i - 1]
         line0 = src[:fn.start()].count("\n") + 1
         nodes, shapes, cases = [], [], []
+        latest = {}   # Rust lets a test shadow `let mul = ..`; give every definition a unique name
+
+        def define(nm):
+            k = f"{nm}#{len(nodes)}"
+            latest[nm] = k
+            return k
+
+        def ref(nm):
+            return latest[nm]
         cur_root = None
         ok = True
         last_case = None
@@ -81,22 +90,22 @@ def parse_tests(path, prefix):
                 continue
             m = re.fullmatch(r"let (\w+) = ctx\.([xyz])\(\);", st)
             if m:
-                nodes.append([m.group(1), "var", [m.group(2)]])
+                nodes.append([define(m.group(1)), "var", [m.group(2)]])
                 continue
             m = re.fullmatch(r"let (\w+) = ctx\.constant\((%s)\);" % NUM, st)
             if m:
-                nodes.append([m.group(1), "const", [num(m.group(2))]])
+                nodes.append([define(m.group(1)), "const", [num(m.group(2))]])
                 continue
             m = re.fullmatch(r"let (\w+) = ctx\.(\w+)\((.*)\)\.unwrap\(\);", st)
             if m:
                 args = []
                 for a in [x.strip() for x in m.group(3).split(",")]:
-                    args.append(a if re.fullmatch(r"[A-Za-z_]\w*", a) else num(a))
-                nodes.append([m.group(1), m.group(2), args])
+                    args.append(ref(a) if re.fullmatch(r"[A-Za-z_]\w*", a) else num(a))
+                nodes.append([define(m.group(1)), m.group(2), args])
                 continue
             m = re.fullmatch(r"let (?:shape|s) = F::new\(&ctx, &\[(\w+)\]\)\.unwrap\(\);", st)
             if m:
-                cur_root = m.group(1)
+                cur_root = ref(m.group(1))
                 continue
             if re.match(r"let (tape|vs|mut eval|eval) = ", st) or st.startswith("use "):
                 continue

@@ -1,0 +1,186 @@
+"""Pins the CPU oracle to the reference's own golden vectors and known-answer
+tests.  CPU only.  Fixtures under tests/golden/ were
+transcribed from the reference by the committed extract_*.py scripts."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from conftest import model_text
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+PIX = json.load(open(os.path.join(GOLD, "pixel_render.json")))
+IVL = json.load(open(os.path.join(GOLD, "interval_known_answers.json")))
+CHOICE = {"Left": 1, "Right": 2, "Both": 3}
+
+
+def ascii_rows(orc, img):
+    return ["".join("#" if b else "." for b in r) for r in orc.pixel_inside(img)]
+
+
+def view2(center, scale):
+    # View2::world_to_model = translation(center) * scaling(scale)  (fidget-gui/src/lib.rs:91-104)
+    return np.array([[scale, 0, center[0]], [0, scale, center[1]], [0, 0, 1]], dtype=np.float32)
+
+
+@pytest.mark.parametrize("n_regs", [255, 3])        # render_tests!(vm, ..) and render_tests!(vm3, ..)
+def test_hi_goldens(orc, n_regs):
+    t = orc.Tape.from_vm(model_text("hi.vm"), n_regs)
+    img, _ = orc.render2d(t, 32, 32)
+    assert ascii_rows(orc, img) == PIX["check_hi:EXPECTED"]["rows"]
+    img, _ = orc.render2d(t, 64, 32)
+    assert ascii_rows(orc, img) == PIX["check_hi_wide:EXPECTED"]["rows"]
+    m = view2((0.5, 0.5), 0.5)                       # prepend_translation(.5,.5); prepend_scaling(.5)
+    img, _ = orc.render2d(t, 32, 32, mat=orc.pixel_mat(32, 32, m))
+    assert ascii_rows(orc, img) == PIX["check_hi_transformed:EXPECTED"]["rows"]
+    assert ascii_rows(orc, img) == PIX["check_hi_bounded:EXPECTED"]["rows"]   # same matrix via View2
+
+
+@pytest.mark.parametrize("n_regs", [255, 3])
+def test_quarter_golden(orc, n_regs):
+    t = orc.Tape.from_vm(model_text("quarter.vm"), n_regs)
+    img, _ = orc.render2d(t, 32, 32)
+    assert ascii_rows(orc, img) == PIX["check_quarter:EXPECTED"]["rows"]
+
+
+@pytest.mark.parametrize("n_regs", [255, 3])
+def test_circle_with_bound_var(orc, n_regs):
+    # fidget/tests/pixel_render.rs:277-364
+    ctx = orc.Context()
+    x, y = ctx.x(), ctx.y()
+    r = ctx.sqrt(ctx.add(ctx.square(x), ctx.square(y)))
+    c, _ = ctx.var()
+    td = ctx.tape(ctx.sub(r, c), n_regs)
+    t = orc.Tape.from_data(td)
+    slot = [i for i, (k, _) in enumerate(td.vars()) if k == "v"][0]
+    for radius, key in ((0.75, "check_circle_var:EXPECTED_075"), (0.5, "check_circle_var:EXPECTED_05")):
+        vv = np.zeros(td.n_vars, dtype=np.float32)
+        vv[slot] = radius
+        img, _ = orc.render2d(t, 32, 32, var_values=vv)
+        assert ascii_rows(orc, img) == PIX[key]["rows"]
+
+
+def test_neg_infinity_pixel_perfect(orc):
+    # pixel_render.rs:366-377
+    ctx = orc.Context()
+    t = orc.Tape.from_data(ctx.tape(ctx.constant(float("-inf"))))
+    img, _ = orc.render2d(t, 256, 256, pixel_perfect=True)
+    assert orc.pixel_inside(img).all()
+
+
+def test_screen_to_world(orc):
+    # fidget-core/src/render/region.rs:204-228
+    m = orc.screen_to_world_2d(1000, 500)
+
+    def tp(x, y):
+        out = np.zeros(3, dtype=np.float32)
+        import ctypes as C
+        orc.lib().orc_transform_f32(m.ctypes.data_as(C.POINTER(C.c_float)), x, y, 0.0,
+                                    out.ctypes.data_as(C.POINTER(C.c_float)))
+        return float(out[0]), float(out[1])
+    assert tp(500.0, 249.0) == (0.0, 0.0)
+    assert tp(500.0, -1.0) == (0.0, 1.0)
+    assert tp(500.0, 499.0) == (0.0, -1.0)
+    assert tp(0.0, 249.0) == (-2.0, 0.0)
+    assert tp(1000.0, 249.0) == (2.0, 0.0)
+
+
+def test_camera_render_config(orc):
+    # pixel_render.rs:429-474
+    import ctypes as C
+    for scale, exp in ((0.5, [(0.0, 1.0), (1.0, 1.0), (1.0, 0.0)]), (0.25, [(0.25, 0.75), (0.75, 0.75), (0.75, 0.25)])):
+        m = np.ascontiguousarray(orc.pixel_mat(512, 512, view2((0.5, 0.5), scale)))
+        for (px, py), e in zip([(0.0, -1.0), (512.0, -1.0), (512.0, 511.0)], exp):
+            out = np.zeros(3, dtype=np.float32)
+            orc.lib().orc_transform_f32(m.ctypes.data_as(C.POINTER(C.c_float)), px, py, 0.0,
+                                        out.ctypes.data_as(C.POINTER(C.c_float)))
+            assert (float(out[0]), float(out[1])) == e
+
+
+def _f(v):
+    return {"nan": math.nan, "inf": math.inf, "-inf": -math.inf}.get(v, v) if isinstance(v, str) else v
+
+
+def _build(ctx, nodes):
+    env = {}
+    for name, op, args in nodes:
+        if op == "var":
+            env[name] = getattr(ctx, args[0])()
+        elif op == "const":
+            env[name] = ctx.constant(float(args[0]))
+        else:
+            a = [env[x] if isinstance(x, str) else float(x) for x in args]
+            env[name] = getattr(ctx, {"and": "and_", "or": "or_", "not": "not_"}.get(op, op))(*a)
+    return env
+
+
+@pytest.mark.parametrize("name", sorted(IVL))
+def test_interval_known_answers(orc, name):
+    """fidget-core/src/eval/test/interval.rs (exact bounds and exact Choice traces)."""
+    spec = IVL[name]
+    ctx = orc.Context()
+    env = _build(ctx, spec["nodes"])
+    tapes = {}
+    for case in spec["cases"]:
+        root = case["root"]
+        if root not in tapes:
+            td = ctx.tape(env[root])
+            tapes[root] = (td, orc.Tape.from_data(td))
+        td, t = tapes[root]
+        vx, vy, vz = td.var_slots()
+        ins = [[_f(a), _f(b)] for a, b in case["inputs"]]
+        vars_ = np.zeros((max(td.n_vars, 1), 2), dtype=np.float32)
+        for slot, iv in zip([s for s in (vx, vy, vz)], ins + [None] * 3):
+            if slot >= 0 and iv is not None:
+                vars_[slot] = iv
+        if td.n_vars == 1:                       # single-variable tests pass `[[a, b].into()]`
+            vars_[0] = ins[0]
+        out, choices, simplify = t.interval_eval(vars_)
+        exp = [_f(v) for v in case["expect"]]
+        if any(isinstance(v, float) and math.isnan(v) for v in exp):
+            assert np.isnan(out).all(), (name, case)
+        else:
+            assert out.tolist() == [np.float32(exp[0]), np.float32(exp[1])], (name, case, out)
+        if "trace" in case:
+            if case["trace"] is None:
+                assert not simplify, (name, case)
+            else:
+                assert simplify and choices.tolist() == [CHOICE[c] for c in case["trace"]], (name, case)
+
+
+def test_interval_contains_point_samples(orc):
+    """Property test in the spirit of interval.rs:1087-1170: for every op, interval results contain
+    point samples (or are the NaN interval)."""
+    from fidget_b200.host import UNARY_OPS, BINARY_OPS
+    rng = np.random.default_rng(0)
+    args = [np.float32(np.pi * 2 * i / 8) for i in range(-8, 9)] + [np.float32(v) for v in (1, 5, .5, 1.5, 10)]
+    for op in UNARY_OPS + BINARY_OPS:
+        if op in ("rand", "mix"):
+            continue
+        ctx = orc.Context()
+        x, y = ctx.x(), ctx.y()
+        node = ctx.unary(op, x) if op in UNARY_OPS else ctx.binary(op, x, y)
+        td = ctx.tape(node)
+        t = orc.Tape.from_data(td)
+        vx, vy, _ = td.var_slots()
+        for _ in range(60):
+            a, b = sorted(rng.choice(args, 2))
+            c, d = sorted(rng.choice(args, 2))
+            box = np.zeros((td.n_vars, 2), dtype=np.float32)
+            box[vx] = (a, b)
+            if vy >= 0:
+                box[vy] = (c, d)
+            out, _, _ = t.interval_eval(box)
+            if np.isnan(out).any():
+                continue
+            px = rng.uniform(a, b, 16).astype(np.float32)
+            py = rng.uniform(c, d, 16).astype(np.float32)
+            pts = [None] * td.n_vars
+            pts[vx] = px
+            if vy >= 0:
+                pts[vy] = py
+            v = t.float_slice_eval(pts)
+            ok = np.isnan(v) | ((v >= out[0] - 1e-5 * max(1, abs(out[0]))) & (v <= out[1] + 1e-5 * max(1, abs(out[1]))))
+            assert ok.all(), (op, box, out, v[~ok])
