@@ -171,13 +171,10 @@ def main():
     tape = ctx.tape(root)
     shape = fb.CudaShape(cuda, tape)
 
+    from fidget_b200.shard import band_rows
     T0 = 128
     n_rows = SIZE // T0
-    if world > 1:
-        assert n_rows % world == 0
-        rows = (rank * n_rows // world, (rank + 1) * n_rows // world)
-    else:
-        rows = (0, 0)
+    rows = band_rows(rank, world, SIZE, T0) if world > 1 else (0, 0)
     cfg = fb.RenderConfig2D(SIZE, SIZE, root_rows=rows)
     image = torch.zeros((SIZE, SIZE), dtype=torch.float32, device=dev)
     gathered = torch.empty_like(image) if world > 1 else None

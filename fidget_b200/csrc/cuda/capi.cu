@@ -628,6 +628,20 @@ int32_t fc_tape_set_axes(fc_tape* t, int32_t x, int32_t y, int32_t z) {
 
 static AxisMap axes_of(const fc_tape* t) { return AxisMap{t->ax[0], t->ax[1], t->ax[2]}; }
 
+// ShapeVars: every non-axis input slot needs a value (MissingVar otherwise, shape/mod.rs:586-600)
+static int32_t bind_vars(const fc_tape* t, const float* values, uint32_t n_values, VarBind& vb) {
+    AxisMap ax = axes_of(t);
+    vb.x = ax.x; vb.y = ax.y; vb.z = ax.z;
+    if (t->info.n_vars > uint32_t(MAX_RENDER_VARS)) return fail(FC_ERR_UNSUPPORTED, "renderers support at most 16 input variables");
+    for (int i = 0; i < MAX_RENDER_VARS; ++i) vb.values[i] = 0.0f;
+    for (uint32_t i = 0; i < t->info.n_vars; ++i) {
+        if (int(i) == ax.x || int(i) == ax.y || int(i) == ax.z) continue;
+        if (i >= n_values) return fail(FC_ERR_INVALID, "missing value for bound variable in input slot " + std::to_string(i));
+        vb.values[i] = values[i];
+    }
+    return FC_OK;
+}
+
 static cudaEvent_t get_event(fc_ctx* c, size_t i) {
     while (c->events.size() <= i) {
         cudaEvent_t ev;
@@ -689,7 +703,8 @@ int32_t fc_render2d(fc_ctx* c, const fc_tape* tape, const fc_render2d_cfg* cfg, 
     if (want_stats) CU(cudaMemsetAsync(c->stats.p, 0, sizeof(Stats), s));
     // (pixels outside the requested band of root rows are left untouched)
 
-    AxisMap ax = axes_of(tape);
+    VarBind vb;
+    if (int32_t vrc = bind_vars(tape, cfg->var_values, cfg->n_var_values, vb)) return vrc;
     size_t ev = 0;
     if (timing) CU(cudaEventRecord(get_event(c, ev++), s));
     uint32_t launches = 0;
@@ -722,7 +737,7 @@ int32_t fc_render2d(fc_ctx* c, const fc_tape* tape, const fc_render2d_cfg* cfg, 
         p.choice_words = choice_words;
         p.ctr = c->counters.as<Counters>();
         p.stats = want_stats ? c->stats.as<Stats>() : nullptr;
-        p.var_x = ax.x; p.var_y = ax.y; p.var_z = ax.z;
+        p.vb = vb;
         int blocks = grid_blocks;
         if (l == 0) {
             uint64_t warps = (n_roots + 31) / 32;
@@ -772,7 +787,7 @@ int32_t fc_render2d(fc_ctx* c, const fc_tape* tape, const fc_render2d_cfg* cfg, 
         q.list = L;
         q.cursor = L;
         q.stats = want_stats ? c->stats.as<Stats>() : nullptr;
-        q.var_x = ax.x; q.var_y = ax.y; q.var_z = ax.z;
+        q.vb = vb;
         launch_pixels_2d(q, c->sm_count * env_int("FIDGET_B200_PIXEL_BLOCKS_PER_SM", 8), s);
         ++launches;
     }
@@ -869,7 +884,8 @@ int32_t fc_render3d(fc_ctx* c, const fc_tape* tape, const fc_render3d_cfg* cfg, 
     CU(cudaMemsetAsync(c->heightmap.p, 0, npix * 8, s));
     if (want_stats) CU(cudaMemsetAsync(c->stats.p, 0, sizeof(Stats), s));
 
-    AxisMap ax = axes_of(tape);
+    VarBind vb;
+    if (int32_t vrc = bind_vars(tape, cfg->var_values, cfg->n_var_values, vb)) return vrc;
     size_t ev = 0;
     if (timing) CU(cudaEventRecord(get_event(c, ev++), s));
     uint32_t launches = 0;
@@ -900,7 +916,7 @@ int32_t fc_render3d(fc_ctx* c, const fc_tape* tape, const fc_render3d_cfg* cfg, 
         p.ctr = c->counters.as<Counters>();
         p.stats = want_stats ? c->stats.as<Stats>() : nullptr;
         p.heightmap = c->heightmap.as<unsigned long long>();
-        p.var_x = ax.x; p.var_y = ax.y; p.var_z = ax.z;
+        p.vb = vb;
         int blocks = grid_blocks;
         if (l == 0) {
             uint64_t warps = (n_roots + 31) / 32;
@@ -921,7 +937,7 @@ int32_t fc_render3d(fc_ctx* c, const fc_tape* tape, const fc_render3d_cfg* cfg, 
         q.ctr = c->counters.as<Counters>();
         q.list = L; q.cursor = L;
         q.stats = want_stats ? c->stats.as<Stats>() : nullptr;
-        q.var_x = ax.x; q.var_y = ax.y; q.var_z = ax.z;
+        q.vb = vb;
         launch_voxels_3d(q, c->sm_count * env_int("FIDGET_B200_PIXEL_BLOCKS_PER_SM", 8), s);
         ++launches;
     }
@@ -935,7 +951,7 @@ int32_t fc_render3d(fc_ctx* c, const fc_tape* tape, const fc_render3d_cfg* cfg, 
         q.heightmap = c->heightmap.as<unsigned long long>();
         q.out = dimg;
         q.stats = want_stats ? c->stats.as<Stats>() : nullptr;
-        q.var_x = ax.x; q.var_y = ax.y; q.var_z = ax.z;
+        q.vb = vb;
         launch_normals_3d(q, s);
         ++launches;
     }

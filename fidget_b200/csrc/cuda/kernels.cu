@@ -31,6 +31,16 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
     return m;
 }
 
+// INPUT clause -> value: the axes get coordinates, other slots their bound value
+template <class T, class F>
+__device__ __forceinline__ T pick_input(const VarBind& vb, uint32_t i, T X, T Y, T Z, F from_float) {
+    const int k = int(i);
+    if (k == vb.x) return X;
+    if (k == vb.y) return Y;
+    if (k == vb.z) return Z;
+    return from_float(vb.values[k & (MAX_RENDER_VARS - 1)]);
+}
+
 struct Dec {
     uint32_t op, form, out, lhs, rhs;
     __device__ __forceinline__ explicit Dec(uint32_t x) {
@@ -328,10 +338,9 @@ k_interval_level(const __grid_constant__ LevelParams p) {
             ChoicePacker pk;
             pk.base = cs;
             itv r = iv_nan();
-            const int ix = p.var_x, iy = p.var_y;
             run_interval(
                 tape, tr.n_ops, slots,
-                [&](uint32_t i) { return int(i) == ix ? vx : (int(i) == iy ? vy : vz); }, pk,
+                [&](uint32_t i) { return pick_input(p.vb, i, vx, vy, vz, [](float f) { return iv1(f); }); }, pk,
                 [&](uint32_t oi, itv v) { if (oi == 0) r = v; });
             pk.finish();
 
@@ -496,9 +505,9 @@ __global__ void __launch_bounds__(128) k_voxels_3d(const __grid_constant__ Voxel
                 xform_f32(p.mat, float(gx0), float(gy0), float(cz + uint32_t(k)), x0, y0, z0);
                 xform_f32(p.mat, float(gx1), float(gy1), float(cz + uint32_t(k)), x1, y1, z1);
                 const float2 X = make_float2(x0, x1), Y = make_float2(y0, y1), Z = make_float2(z0, z1);
-                const int ix = p.var_x, iy = p.var_y;
-                const float2 r = run_f32x2(tape, tr.n_ops, slots,
-                                           [&](uint32_t i) { return int(i) == ix ? X : (int(i) == iy ? Y : Z); });
+                const float2 r = run_f32x2(tape, tr.n_ops, slots, [&](uint32_t i) {
+                    return pick_input(p.vb, i, X, Y, Z, [](float f) { return make_float2(f, f); });
+                });
                 const unsigned long long key = ((unsigned long long)(cz + uint32_t(k) + 1u) << 32) | id;
                 if (!done0) {
                     ++shaded;
@@ -574,9 +583,9 @@ __global__ void __launch_bounds__(128) k_normals_3d(const __grid_constant__ Norm
         grd gx, gy, gz;
         xform_gr(p.mat, gr(float(x), 1.0f, 0.0f, 0.0f), gr(float(y), 0.0f, 1.0f, 0.0f),
                  gr(float(depth - 1u), 0.0f, 0.0f, 1.0f), gx, gy, gz);
-        const int ix = p.var_x, iy = p.var_y;
-        const grd r = run_grad(tr.ptr, tr.n_ops, slots,
-                               [&](uint32_t i) { return int(i) == ix ? gx : (int(i) == iy ? gy : gz); });
+        const grd r = run_grad(tr.ptr, tr.n_ops, slots, [&](uint32_t i) {
+            return pick_input(p.vb, i, gx, gy, gz, [](float f) { return gr1(f); });
+        });
         if (mine) { g = r; pending = false; ++n; }
     }
     if (inb) {
@@ -644,9 +653,9 @@ __global__ void __launch_bounds__(128) k_pixels_2d(const __grid_constant__ Pixel
             xform_f32(p.mat, float(cx + i0), float(cy + j0), p.z2d, x0, y0, z0);
             xform_f32(p.mat, float(cx + i1), float(cy + j1), p.z2d, x1, y1, z1);
             const float2 X = make_float2(x0, x1), Y = make_float2(y0, y1), Z = make_float2(z0, z1);
-            const int ix = p.var_x, iy = p.var_y;
-            float2 r = run_f32x2(tape, tr.n_ops, slots,
-                                 [&](uint32_t i) { return int(i) == ix ? X : (int(i) == iy ? Y : Z); });
+            float2 r = run_f32x2(tape, tr.n_ops, slots, [&](uint32_t i) {
+                return pick_input(p.vb, i, X, Y, Z, [](float f) { return make_float2(f, f); });
+            });
             // RawDistancePixel::from(f32): canonical NaN (pixel.rs:234-240)
             if (r.x != r.x) r.x = nanf_();
             if (r.y != r.y) r.y = nanf_();
@@ -932,8 +941,6 @@ k_interval_root_coop_2d(const __grid_constant__ LevelParams p) {
         itv vx, vy, vz;
         xform_iv(p.mat, iv(float(cx), float(cx) + float(T)), iv(float(cy), float(cy) + float(T)), iv(p.z2d, p.z2d),
                  vx, vy, vz);
-        const int ix = p.var_x, iy = p.var_y;
-
         auto put_choice = [&](uint32_t cidx, uint32_t c) {
             atomicOr(&chs[cidx >> 4], c << ((cidx & 15u) * 2u));
             if (c != 3u) s_nonboth = 1u;
@@ -957,7 +964,7 @@ k_interval_root_coop_2d(const __grid_constant__ LevelParams p) {
             } else if (d.op == OP_COPY) {
                 r = d.form == F_RI ? iv1(imm) : sl;
             } else if (d.op == OP_INPUT) {
-                r = int(rc.y) == ix ? vx : (int(rc.y) == iy ? vy : vz);
+                r = pick_input(p.vb, rc.y, vx, vy, vz, [](float f) { return iv1(f); });
             } else {
                 if (rc.y == 0) s_res = sl;
                 r = sl;

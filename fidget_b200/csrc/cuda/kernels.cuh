@@ -79,6 +79,14 @@ struct CoopSched {
     CoopSeg segs[COOP_MAX_SEGS];
 };
 
+// Where the renderers feed coordinates: input slots of X, Y, Z (-1 = unused) and the
+// values bound to every other input slot (ShapeVars, shape/mod.rs:548-640).
+constexpr int MAX_RENDER_VARS = 16;
+struct VarBind {
+    int x, y, z;
+    float values[MAX_RENDER_VARS];
+};
+
 struct LevelParams {
     CoopSched sched;
     int level;                 // index into tile sizes
@@ -112,8 +120,7 @@ struct LevelParams {
     Stats* stats;
     // 3D
     unsigned long long* heightmap;  // 3D: width*height keys (depth << 32 | leaf job id + 1), atomicMax
-    uint32_t n_vars;
-    int var_x, var_y, var_z;
+    VarBind vb;
 };
 
 struct PixelParams {
@@ -127,7 +134,7 @@ struct PixelParams {
     int list;                  // which n_jobs entry holds the leaf count
     int cursor;
     Stats* stats;
-    int var_x, var_y, var_z;
+    VarBind vb;
 };
 
 struct FillParams {
@@ -146,7 +153,7 @@ struct VoxelParams {
     Counters* ctr;
     int list, cursor;
     Stats* stats;
-    int var_x, var_y, var_z;
+    VarBind vb;
 };
 struct NormalParams {
     uint32_t width, height, depth;
@@ -156,7 +163,7 @@ struct NormalParams {
     const unsigned long long* heightmap;
     void* out;                  // GeometryPixel[width*height]
     Stats* stats;
-    int var_x, var_y, var_z;
+    VarBind vb;
 };
 
 // launchers (kernels.cu)

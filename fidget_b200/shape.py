@@ -284,6 +284,7 @@ class RenderConfig2D:
     mat: np.ndarray | None = None               # full 4x4 override
     root_rows: tuple = (0, 0)                   # band of root-tile rows (multi-GPU)
     timing: bool = False
+    var_values: tuple = ()                      # ShapeVars: value per tape input slot (axis slots ignored)
 
     def matrix(self):
         return self.mat if self.mat is not None else pixel_mat(self.width, self.height, self.world_to_model)
@@ -299,6 +300,7 @@ class RenderConfig3D:
     mat: np.ndarray | None = None
     z_range: tuple = (0, 0)
     timing: bool = False
+    var_values: tuple = ()
     clamp: bool = True                          # False for slab renders (fc_merge_slabs applies it)
 
     def matrix(self):
@@ -320,6 +322,9 @@ def render2d(shape: CudaShape, cfg: RenderConfig2D, out=None, stats: bool = Fals
         c.tile_sizes[i] = t
     c.flags = (_lib.FC_FLAG_TIMING if cfg.timing else 0) | (_lib.FC_FLAG_ASYNC if asynchronous else 0)
     c.root_row_begin, c.root_row_end = cfg.root_rows
+    c.n_var_values = len(cfg.var_values)
+    for i, v in enumerate(cfg.var_values):
+        c.var_values[i] = float(v)
     if out is None:
         out = np.zeros((cfg.height, cfg.width), dtype=np.float32)
     st = _lib.FcRenderStats() if stats else None
@@ -339,6 +344,9 @@ def render3d(shape: CudaShape, cfg: RenderConfig3D, out=None, stats: bool = Fals
     c.flags = (_lib.FC_FLAG_TIMING if cfg.timing else 0) | (_lib.FC_FLAG_ASYNC if asynchronous else 0) | \
         (0 if cfg.clamp else _lib.FC_FLAG_NO_CLAMP)
     c.z_begin, c.z_end = cfg.z_range
+    c.n_var_values = len(cfg.var_values)
+    for i, v in enumerate(cfg.var_values):
+        c.var_values[i] = float(v)
     if out is None:
         out = np.zeros((cfg.height, cfg.width), dtype=GEOMETRY_PIXEL)
     st = _lib.FcRenderStats() if stats else None

@@ -132,6 +132,7 @@ int32_t fc_simplify(fc_eval* e, const fc_tape* parent, const uint8_t* choices, s
 
 /* ---- fused renderers (the measured path) -------------------------------- */
 #define FC_MAX_TILE_LEVELS 8
+#define FC_MAX_VARS 16
 #define FC_FLAG_ASYNC 1u        /* enqueue only; errors surface in fc_ctx_synchronize */
 #define FC_FLAG_TIMING 2u       /* record per-stage CUDA events (fc_render_stats.stage_ms) */
 #define FC_FLAG_NO_CLAMP 4u     /* fc_render3d: skip the final depth clamp (slab renders; fc_merge_slabs applies it) */
@@ -148,6 +149,10 @@ typedef struct fc_render2d_cfg {
     /* Y band [row_begin,row_end) of root-tile rows to render (multi-GPU
      * sharding); row_end = 0 means all rows. */
     uint32_t root_row_begin, root_row_end;
+    /* ShapeVars (shape/mod.rs:548-640): value for each tape input slot that is not an axis
+     * (entries at axis slots are ignored); n_var_values may be 0 for plain X/Y/Z shapes. */
+    uint32_t n_var_values;
+    float var_values[FC_MAX_VARS];
 } fc_render2d_cfg;
 
 typedef struct fc_geometry_pixel { float normal[3]; uint32_t depth; } fc_geometry_pixel; /* voxel.rs:126-134 */
@@ -161,6 +166,8 @@ typedef struct fc_render3d_cfg {
     /* Z slab [z_begin,z_end) in voxels (multiples of tile_sizes[0]);
      * z_end = 0 means the whole depth. */
     uint32_t z_begin, z_end;
+    uint32_t n_var_values;      /* as in fc_render2d_cfg */
+    float var_values[FC_MAX_VARS];
 } fc_render3d_cfg;
 
 typedef struct fc_render_stats {

@@ -1,0 +1,63 @@
+"""The C-ABI library loads on a CPU-only machine and exports every symbol that
+include/fidget_cuda.h and csrc/host/host_capi.h declare.  No compute calls."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared(header, prefix):
+    text = open(os.path.join(ROOT, header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    return sorted(set(re.findall(r"\b(%s\w+)\s*\(" % prefix, text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from fidget_b200 import _lib
+    lib = _lib.load()
+    names = declared("include/fidget_cuda.h", "fc_") + declared("fidget_b200/csrc/host/host_capi.h", "fh_")
+    assert len(names) > 35
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    # the Python binding table covers the whole CUDA header too
+    assert sorted(_lib.CUDA_API) == declared("include/fidget_cuda.h", "fc_")
+    assert lib.fc_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    from fidget_b200 import _lib
+    assert C.sizeof(_lib.FcTapeInfo) == 7 * 4
+    assert C.sizeof(_lib.FcRender2dCfg) == 4 * 2 + 64 + 4 + 4 + 4 + 32 + 4 + 8 + 4 + 64
+    assert C.sizeof(_lib.FcRender3dCfg) == 4 * 3 + 64 + 4 + 32 + 4 + 8 + 4 + 64
+    assert C.sizeof(_lib.FcRenderStats) == 5 * 64 + 3 * 8 + 4 + 16 * 4 + 4  # + tail padding to 8
+
+
+def test_no_silent_cpu_fallback():
+    """Without a usable GPU the backend must fail loudly (FC_ERR_NO_DEVICE)."""
+    import fidget_b200 as fb
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("a GPU is present")
+    with pytest.raises(fb.CudaError) as e:
+        fb.CudaContext(0)
+    assert e.value.code == -5 and "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under fidget_b200/ may reference it."""
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "fidget_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cc", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                if re.search(r"(?m)^\s*(from|import)\s+oracle|#include\s+[\"<].*oracle", text):
+                    bad.append(f)
+    assert not bad, bad

@@ -216,3 +216,109 @@ def test_render3d_slabs_merge_to_full_image(cuda):
     merged = out.cpu().numpy().view(fb.GEOMETRY_PIXEL).reshape(size, size)
     assert np.array_equal(merged["depth"], full["depth"])
     assert same_f32(merged["normal"], full["normal"])
+
+
+# ---------------------------------------------------------------------------
+# Reference golden images through the CUDA path (fidget/tests/pixel_render.rs:70-385)
+import json
+import os
+
+_PIX = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pixel_render.json")))
+
+
+def _rows(img):
+    return ["".join("#" if b else "." for b in r) for r in fb.pixel_inside(img)]
+
+
+def _view2(center, scale):
+    return np.array([[scale, 0, center[0]], [0, scale, center[1]], [0, 0, 1]], dtype=np.float32)
+
+
+def test_golden_hi_variants(cuda):
+    gs = fb.CudaShape.from_vm(cuda, model_text("hi.vm"))
+    assert _rows(fb.render2d(gs, fb.RenderConfig2D(32, 32))) == _PIX["check_hi:EXPECTED"]["rows"]
+    assert _rows(fb.render2d(gs, fb.RenderConfig2D(64, 32))) == _PIX["check_hi_wide:EXPECTED"]["rows"]
+    cfg = fb.RenderConfig2D(32, 32, world_to_model=_view2((0.5, 0.5), 0.5))
+    assert _rows(fb.render2d(gs, cfg)) == _PIX["check_hi_transformed:EXPECTED"]["rows"]
+    assert _rows(fb.render2d(gs, cfg)) == _PIX["check_hi_bounded:EXPECTED"]["rows"]
+
+
+def test_golden_quarter(cuda):
+    gs = fb.CudaShape.from_vm(cuda, model_text("quarter.vm"))
+    assert _rows(fb.render2d(gs, fb.RenderConfig2D(32, 32))) == _PIX["check_quarter:EXPECTED"]["rows"]
+
+
+def test_golden_circle_with_bound_var(cuda):
+    ctx = fb.Context()
+    x, y = ctx.x(), ctx.y()
+    r = ctx.sqrt(ctx.add(ctx.square(x), ctx.square(y)))
+    c, _ = ctx.var()
+    td = ctx.tape(ctx.sub(r, c))
+    gs = fb.CudaShape(cuda, td)
+    slot = [i for i, (k, _) in enumerate(td.vars()) if k == "v"][0]
+    for radius, key in ((0.75, "check_circle_var:EXPECTED_075"), (0.5, "check_circle_var:EXPECTED_05")):
+        vv = [0.0] * td.n_vars
+        vv[slot] = radius
+        assert _rows(fb.render2d(gs, fb.RenderConfig2D(32, 32, var_values=tuple(vv)))) == _PIX[key]["rows"]
+    with pytest.raises(fb.CudaError):           # MissingVar
+        fb.render2d(gs, fb.RenderConfig2D(32, 32))
+
+
+def test_golden_neg_infinity_pixel_perfect(cuda):
+    ctx = fb.Context()
+    gs = fb.CudaShape(cuda, ctx.tape(ctx.constant(float("-inf"))))
+    img = fb.render2d(gs, fb.RenderConfig2D(256, 256, pixel_perfect=True))
+    assert fb.pixel_inside(img).all()
+
+
+def test_host_transforms_match_oracle(orc):
+    for w, h in ((32, 32), (64, 32), (1000, 500), (4096, 4096)):
+        assert np.array_equal(fb.pixel_mat(w, h), orc.pixel_mat(w, h))
+        m = _view2((0.5, 0.25), 0.3)
+        assert np.array_equal(fb.pixel_mat(w, h, m), orc.pixel_mat(w, h, m))
+    assert np.array_equal(fb.voxel_mat(128, 256, 64), orc.voxel_mat(128, 256, 64))
+
+
+@pytest.mark.parametrize("name", ["hi.vm", "colonnade.vm", "prospero.vm"])
+def test_spilled_tapes_evaluate_like_the_oracle(orc, cuda, name):
+    """GenericVmFunction<3>-style tapes (Load/Store) through the trait-level evaluators."""
+    text = model_text(name)
+    ot, gs = orc.Tape.from_vm(text, 3), fb.CudaShape.from_vm(cuda, text, 3)
+    assert gs.info.mem_count > 0
+    pts = _points(1025, ot.n_vars, 7)
+    assert same_f32(gs.float_slice_eval(pts), ot.float_slice_eval(pts))
+    boxes = _boxes(65, ot.n_vars, 11)
+    out, ch, simp = gs.interval_eval_batch(boxes, want_choices=True)
+    for i in range(boxes.shape[0]):
+        o, oc, os_ = ot.interval_eval(boxes[i])
+        assert same_f32(out[i, 0], o) and np.array_equal(ch[i], oc) and bool(simp[i]) == os_
+    with pytest.raises(fb.CudaError):           # renderers refuse spilled tapes loudly
+        fb.render2d(gs, fb.RenderConfig2D(64, 64))
+
+
+def test_grad_slice_matches_oracle(orc, cuda):
+    for name, exact in (("prospero.vm", True), ("colonnade.vm", True), ("bear.vm", False)):
+        ot, gs = _pair(orc, cuda, name)
+        rng = np.random.default_rng(2)
+        n = 515
+        vars_ = []
+        for k in range(ot.n_vars):
+            g = np.zeros((n, 4), dtype=np.float32)
+            g[:, 0] = rng.uniform(-1, 1, n)
+            g[:, 1 + k] = 1.0
+            vars_.append(g)
+        g, o = gs.grad_slice_eval(vars_), ot.grad_slice_eval(vars_)
+        if exact:
+            assert same_f32(g, o), name
+        else:
+            assert np.allclose(g, o, rtol=1e-5, atol=1e-5, equal_nan=True)
+
+
+def test_point_eval_matches_oracle(orc, cuda):
+    ot, gs = _pair(orc, cuda, "hi.vm")
+    rng = np.random.default_rng(4)
+    for _ in range(32):
+        v = rng.uniform(-1, 1, ot.n_vars).astype(np.float32)
+        g, gc, gsim = gs.point_eval(v)
+        o, oc, osim = ot.point_eval(v)
+        assert same_f32(g[0], o) and np.array_equal(gc, oc) and gsim == osim
