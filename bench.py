@@ -226,8 +226,8 @@ def main():
         _, stats = fb.render2d(shape, tcfg, out=image, stats=True)
         stage += np.array(stats["stage_ms"])
     stage /= reps
-    names = {0: "k_interval_level_2d[L0,128px]", 1: "k_interval_level_2d[L1,32px]",
-             2: "k_interval_level_2d[L2,8px]", 8: "k_fill_2d (x3)", 9: "k_pixels_2d"}
+    names = {0: "k_interval_root_coop_2d[L0,128px]", 1: "k_interval_level<2>[L1,32px]",
+             2: "k_interval_level<2>[L2,8px]", 8: "k_fill_2d (x3)", 9: "k_pixels_2d"}
     dom = max(names, key=lambda k: stage[k])
     frac_rows = (rows[1] - rows[0]) / n_rows if world > 1 else 1.0
     # units decided by one launch of the dominant kernel (DESIGN.md "Measurement")

@@ -63,6 +63,25 @@ class FcRenderStats(C.Structure):
         return d
 
 
+class FcOctreeCfg(C.Structure):
+    _fields_ = [("depth", C.c_uint32), ("has_transform", C.c_uint32), ("world_to_model", C.c_float * 16),
+                ("flags", C.c_uint32), ("n_var_values", C.c_uint32), ("var_values", C.c_float * 16)]
+
+
+class FcOctreeStats(C.Structure):
+    _fields_ = [(n, C.c_uint64 * 16) for n in ("evaluated", "full", "empty", "ambiguous")] + \
+               [(n, C.c_uint64) for n in ("leaf_empty", "leaf_full", "leaf_surface", "float_points", "grad_points",
+                                          "arena_bytes_used")] + \
+               [("kernel_launches", C.c_uint32), ("total_ms", C.c_float)]
+
+    def as_dict(self):
+        d = {n: list(getattr(self, n)) for n in ("evaluated", "full", "empty", "ambiguous")}
+        for n in ("leaf_empty", "leaf_full", "leaf_surface", "float_points", "grad_points", "arena_bytes_used",
+                  "kernel_launches", "total_ms"):
+            d[n] = getattr(self, n)
+        return d
+
+
 FC_FLAG_ASYNC = 1
 FC_FLAG_TIMING = 2
 FC_FLAG_NO_CLAMP = 4
@@ -95,6 +114,7 @@ CUDA_API = {
     "fc_render2d": (_i32, [_vp, _vp, _P(FcRender2dCfg), _vp, _P(FcRenderStats)]),
     "fc_render3d": (_i32, [_vp, _vp, _P(FcRender3dCfg), _vp, _P(FcRenderStats)]),
     "fc_merge_slabs": (_i32, [_vp, _P(_vp), _u32, _u32, _u32, _u32, _vp]),
+    "fc_octree_sample": (_i32, [_vp, _vp, _P(FcOctreeCfg), _vp, _u64, _P(_u64), _P(FcOctreeStats)]),
 }
 
 

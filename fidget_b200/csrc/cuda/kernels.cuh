@@ -7,7 +7,7 @@
 
 namespace fdev {
 
-constexpr int MAX_LEVELS = 8;
+constexpr int MAX_LEVELS = 16;             // 3D renders use <= 8; the octree sampler uses depth + 1
 constexpr int WARPS_PER_BLOCK = 4;          // interval kernels
 constexpr int REG_SLOTS = 256;              // register slots of the fast interpreters
 
@@ -118,6 +118,10 @@ struct LevelParams {
     uint32_t choice_words;          // words per lane
     Counters* ctr;
     Stats* stats;
+    // octree sampler (mode 1): coordinates are cells at the finest depth; bounds = coord * cell_h - 1
+    uint32_t mode;
+    uint32_t has_transform;
+    float cell_h;
     // 3D
     unsigned long long* heightmap;  // 3D: width*height keys (depth << 32 | leaf job id + 1), atomicMax
     VarBind vb;
@@ -166,7 +170,33 @@ struct NormalParams {
     VarBind vb;
 };
 
+// One leaf of the Manifold-Dual-Contouring octree (LeafHermiteData, fidget-mesh/src/octree.rs:864-900)
+struct OctreeLeaf {
+    uint16_t ix, iy, iz;
+    uint8_t mask, n_edges;
+    uint16_t present, pad;
+    float pos[12][3];
+    float grad[12][4];   // dx, dy, dz, v
+};
+struct OctreeLeafParams {
+    const TileJob* jobs;
+    uint32_t cap_jobs;
+    Counters* ctr;
+    int list, cursor;
+    float cell_h;
+    uint32_t has_transform;
+    Mat4 mat;
+    VarBind vb;
+    OctreeLeaf* out;
+    TapeRef* out_tapes;         // tape of each emitted leaf (consumed by the gradient pass)
+    uint32_t cap_out;
+    uint32_t* n_out;            // device counter
+    unsigned long long* stats;  // [0] leaf_empty [1] leaf_full [2] leaf_surface [3] float points [4] grad points
+};
+
 // launchers (kernels.cu)
+void launch_octree_leaf(const OctreeLeafParams& p, int blocks, cudaStream_t s);
+void launch_octree_grads(const OctreeLeafParams& p, int blocks, cudaStream_t s);
 void launch_interval_level_3d(const LevelParams& p, int blocks, cudaStream_t s);
 void launch_voxels_3d(const VoxelParams& p, int blocks, cudaStream_t s);
 void launch_normals_3d(const NormalParams& p, cudaStream_t s);

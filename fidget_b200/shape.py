@@ -354,6 +354,41 @@ def render3d(shape: CudaShape, cfg: RenderConfig3D, out=None, stats: bool = Fals
     return (out, st.as_dict()) if stats else out
 
 
+OCTREE_LEAF = np.dtype([("ix", np.uint16), ("iy", np.uint16), ("iz", np.uint16), ("mask", np.uint8),
+                        ("n_edges", np.uint8), ("present", np.uint16), ("pad", np.uint16),
+                        ("pos", np.float32, (12, 3)), ("grad", np.float32, (12, 4))])
+
+
+def octree_sample(shape: CudaShape, depth: int, world_to_model=None, capacity: int | None = None,
+                  stats: bool = False, timing: bool = False, var_values=()):
+    """Sampler half of ``fidget_mesh::Octree::build`` (octree.rs:521-808): surface leaves with their
+    corner mask and per-edge Hermite data, sorted by (iz, iy, ix)."""
+    lib = shape._lib
+    c = _lib.FcOctreeCfg()
+    c.depth = depth
+    if world_to_model is not None:
+        c.has_transform = 1
+        c.world_to_model[:] = np.ascontiguousarray(world_to_model, dtype=np.float32).reshape(16).tolist()
+    c.flags = _lib.FC_FLAG_TIMING if timing else 0
+    c.n_var_values = len(var_values)
+    for i, v in enumerate(var_values):
+        c.var_values[i] = float(v)
+    cap = capacity if capacity is not None else max(1024, min(8 ** depth, 6 * 4 ** depth))
+    st = _lib.FcOctreeStats()
+    while True:
+        out = np.zeros(cap, dtype=OCTREE_LEAF)
+        n = C.c_uint64()
+        rc = lib.fc_octree_sample(shape.cuda._h, shape._h, C.byref(c), _ptr(out), cap, C.byref(n), C.byref(st))
+        if rc != 0 and n.value > cap and capacity is None:
+            cap = int(n.value)          # retry once with the exact count
+            continue
+        _ck(rc)
+        break
+    leaves = out[:n.value]
+    leaves = leaves[np.lexsort((leaves["ix"], leaves["iy"], leaves["iz"]))]
+    return (leaves, st.as_dict()) if stats else leaves
+
+
 def pixel_inside(img: np.ndarray) -> np.ndarray:
     """RawDistancePixel::inside (pixel.rs:177-183)."""
     bits = img.view(np.uint32)

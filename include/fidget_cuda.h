@@ -198,6 +198,41 @@ int32_t fc_render3d(fc_ctx* ctx, const fc_tape* tape, const fc_render3d_cfg* cfg
 int32_t fc_merge_slabs(fc_ctx* ctx, const fc_geometry_pixel* const* slabs, uint32_t n_slabs,
                        uint32_t width, uint32_t height, uint32_t depth, fc_geometry_pixel* out);
 
+/* ---- octree sampler (fidget-mesh) ----------------------------------------- */
+/* The sampling half of Octree::build (fidget-mesh/src/octree.rs:521-808): interval
+ * descent of the [-1,1]^3 octree with tape simplification at every cell, then for
+ * each surface leaf the corner mask, the 16-ary edge searches and the gradient at
+ * every intersection -- i.e. LeafHermiteData.intersections.  QEF solve, cell
+ * collapse and walk_dual stay on the host. */
+#define FC_MAX_OCTREE_DEPTH 12
+typedef struct fc_octree_cfg {
+    uint32_t depth;             /* mesh::Settings::depth */
+    uint32_t has_transform;     /* 0 when Settings::world_to_model is the identity (octree.rs:493-498) */
+    float world_to_model[16];   /* row-major 4x4 */
+    uint32_t flags;
+    uint32_t n_var_values;
+    float var_values[FC_MAX_VARS];
+} fc_octree_cfg;
+typedef struct fc_octree_leaf {
+    uint16_t ix, iy, iz;        /* cell coordinates at `depth` */
+    uint8_t mask;               /* CellMask: bit c = corner c inside (bit 0 of c = +X, 1 = +Y, 2 = +Z) */
+    uint8_t n_edges;
+    uint16_t present, pad;      /* bit e = undirected edge e (types.rs:208-219) carries an intersection */
+    float pos[12][3];           /* LeafIntersection::pos.xyz */
+    float grad[12][4];          /* LeafIntersection::grad = (dx, dy, dz, v) */
+} fc_octree_leaf;
+typedef struct fc_octree_stats {
+    uint64_t evaluated[16], full[16], empty[16], ambiguous[16];   /* interval census per depth */
+    uint64_t leaf_empty, leaf_full, leaf_surface, float_points, grad_points;
+    uint64_t arena_bytes_used;
+    uint32_t kernel_launches;
+    float total_ms;             /* FC_FLAG_TIMING */
+} fc_octree_stats;
+/* out: `cap` leaves, host or device; leaves arrive in no particular order.  *n_leaves receives
+ * the number of surface leaves (if it exceeds cap the call fails with FC_ERR_INVALID). */
+int32_t fc_octree_sample(fc_ctx* ctx, const fc_tape* tape, const fc_octree_cfg* cfg, fc_octree_leaf* out,
+                         uint64_t cap, uint64_t* n_leaves, fc_octree_stats* stats /* may be NULL */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,6 +5,7 @@
 #include <string>
 
 #include "../fidget_b200/csrc/host/host_capi.h"
+#include "octree.h"
 #include "vm.h"
 
 using namespace oracle;
@@ -149,5 +150,30 @@ int32_t orc_render3d(const orc_tape* t, uint32_t w, uint32_t h, uint32_t d, cons
         copy_stats(s, stats);
     });
 }
+
+// Octree sampler.  leaves: buffer of `cap` OctreeLeaf (348 bytes each) or NULL to count.
+int32_t orc_octree_sample(const orc_tape* t, uint32_t depth, const float* world_to_model16, void* leaves, uint64_t cap,
+                          uint64_t* n_leaves, uint64_t* stats /* [16*4 + 5] */) {
+    ORC_TRY({
+        OctreeConfig cfg;
+        cfg.depth = depth;
+        if (world_to_model16) { cfg.has_transform = true; cfg.world_to_model = to_mat(world_to_model16); }
+        std::vector<OctreeLeaf> out;
+        OctreeStats st;
+        octree_sample(t->t, cfg, out, &st);
+        if (n_leaves) *n_leaves = out.size();
+        if (leaves) {
+            if (cap < out.size()) throw std::runtime_error("leaf buffer too small");
+            memcpy(leaves, out.data(), out.size() * sizeof(OctreeLeaf));
+        }
+        if (stats) {
+            memcpy(stats, st.evaluated, 16 * 8); memcpy(stats + 16, st.full, 16 * 8);
+            memcpy(stats + 32, st.empty, 16 * 8); memcpy(stats + 48, st.ambiguous, 16 * 8);
+            stats[64] = st.leaf_empty; stats[65] = st.leaf_full; stats[66] = st.leaf_surface;
+            stats[67] = st.float_points; stats[68] = st.grad_points;
+        }
+    });
+}
+static_assert(sizeof(OctreeLeaf) == 348, "OctreeLeaf layout");
 
 }  // extern "C"

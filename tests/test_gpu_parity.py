@@ -322,3 +322,69 @@ def test_point_eval_matches_oracle(orc, cuda):
         g, gc, gsim = gs.point_eval(v)
         o, oc, osim = ot.point_eval(v)
         assert same_f32(g[0], o) and np.array_equal(gc, oc) and gsim == osim
+
+
+# ---------------------------------------------------------------------------
+# Octree sampler (fidget-mesh Octree::build, sampling half)
+def _cmp_leaves(g, o, exact):
+    assert len(g) == len(o)
+    for k in ("ix", "iy", "iz", "mask", "n_edges", "present"):
+        assert np.array_equal(g[k], o[k]), k
+    present = ((o["present"][:, None] >> np.arange(12)[None, :]) & 1).astype(bool)
+    if exact:
+        assert same_f32(g["pos"][present], o["pos"][present])
+        assert same_f32(g["grad"][present], o["grad"][present])
+    else:
+        assert np.allclose(g["pos"][present], o["pos"][present], rtol=1e-5, atol=1e-6)
+        assert np.allclose(g["grad"][present], o["grad"][present], rtol=1e-4, atol=1e-4, equal_nan=True)
+
+
+@pytest.mark.parametrize("depth", [3, 5])
+def test_octree_sphere_matches_oracle(orc, cuda, depth):
+    ot = orc.Tape.from_data(_sphere_tape(orc.Context, 0.6))
+    gs = fb.CudaShape(cuda, _sphere_tape(fb.Context, 0.6))
+    o, ost = orc.octree_sample(ot, depth)
+    g, gst = fb.octree_sample(gs, depth, stats=True)
+    _cmp_leaves(g, o, exact=True)
+    for k in ("evaluated", "full", "empty", "ambiguous"):
+        assert gst[k][:depth + 1] == ost[k][:depth + 1], k
+    assert (gst["leaf_empty"], gst["leaf_full"], gst["leaf_surface"]) == (ost["leaf_empty"], ost["leaf_full"], ost["leaf_surface"])
+    # analytic check (fidget/tests/octree.rs:9-30 style): intersections lie on the sphere, gradients are unit normals
+    present = ((g["present"][:, None] >> np.arange(12)[None, :]) & 1).astype(bool)
+    r = np.linalg.norm(g["pos"][present], axis=-1)
+    assert np.all(np.abs(r - 0.6) < 2.0 / 2 ** depth / 16 ** 3 + 1e-5)
+    n = g["grad"][present][:, :3]
+    assert np.allclose(np.linalg.norm(n, axis=-1), 1.0, atol=1e-4)
+
+
+def test_octree_colonnade_and_transform(orc, cuda):
+    ot, gs = _pair(orc, cuda, "colonnade.vm")
+    o, _ = orc.octree_sample(ot, 5)
+    g = fb.octree_sample(gs, 5)
+    _cmp_leaves(g, o, exact=True)
+    m = np.eye(4, dtype=np.float32)
+    m[0, 0] = m[1, 1] = m[2, 2] = 0.75
+    m[0, 3] = 0.125
+    o, _ = orc.octree_sample(ot, 4, world_to_model=m)
+    g = fb.octree_sample(gs, 4, world_to_model=m)
+    _cmp_leaves(g, o, exact=True)
+
+
+def test_octree_gyroid_sphere(orc, cuda):
+    """BASELINE config 4's model at a depth the oracle finishes quickly; sin/cos => tolerance on values,
+    and cells whose corner samples sit within an ulp of zero may flip, so compare the common leaves."""
+    ot, gs = _pair(orc, cuda, "gyroid-sphere.vm")
+    o, _ = orc.octree_sample(ot, 6)
+    g = fb.octree_sample(gs, 6)
+    key = lambda a: (a["iz"].astype(np.int64) << 32) | (a["iy"].astype(np.int64) << 16) | a["ix"]
+    ko, kg = key(o), key(g)
+    common = np.intersect1d(ko, kg)
+    assert len(common) > 0.999 * max(len(o), len(g))
+    oc, gc = o[np.isin(ko, common)], g[np.isin(kg, common)]
+    same_mask = oc["mask"] == gc["mask"]
+    assert same_mask.mean() > 0.999
+    oc, gc = oc[same_mask], gc[same_mask]
+    present = ((oc["present"][:, None] >> np.arange(12)[None, :]) & 1).astype(bool)
+    cell = 2.0 / 2 ** 6
+    assert np.all(np.abs(gc["pos"][present] - oc["pos"][present]) <= cell / 1000)   # the 16^4-ary search may land one bracket apart
+    assert np.isclose(gc["grad"][present], oc["grad"][present], rtol=1e-2, atol=1e-2).mean() > 0.999
