@@ -43,6 +43,7 @@ __device__ __forceinline__ T pick_input(const VarBind& vb, uint32_t i, T X, T Y,
 
 struct Dec {
     uint32_t op, form, out, lhs, rhs;
+    Dec() = default;
     __device__ __forceinline__ explicit Dec(uint32_t x) {
         uint32_t dop = x & 0xffu;
         op = dop >> 2;
@@ -57,29 +58,39 @@ struct Dec {
 // Interval interpreter.  `Input` maps a variable index to an interval,
 // `Sink` receives one choice per choice clause in evaluation order, `Out`
 // receives (output index, value).
+// The loop is software-pipelined: while clause i executes, clause i+1 is already
+// decoded and its operands are being loaded from the register file (local
+// memory); an operand that is the result of clause i is forwarded in registers
+// instead of taking the store -> load round trip.
 template <class Input, class Sink, class Out>
 __device__ __forceinline__ void run_interval(const uint2* __restrict__ tape, uint32_t n_ops, itv* slots,
                                              Input input, Sink& sink, Out out_fn) {
     if (n_ops == 0) return;
     uint2 w = __ldg(tape);
+    uint2 w1 = __ldg(tape + (n_ops > 1 ? 1 : 0));
+    Dec d(w.x);
+    itv sl = slots[d.lhs], sr = slots[d.rhs];
     for (uint32_t i = 0; i < n_ops; ++i) {
-        uint2 nxt = __ldg(tape + (i + 1 < n_ops ? i + 1 : i));
-        Dec d(w.x);
-        float imm = __uint_as_float(w.y);
-        itv sl = slots[d.lhs], sr = slots[d.rhs];
-        itv a = d.form == F_IR ? iv1(imm) : sl;
-        itv b = d.form == F_RI ? iv1(imm) : sr;
+        const uint2 w2 = __ldg(tape + (i + 2 < n_ops ? i + 2 : n_ops - 1));
+        const Dec nd(w1.x);
+        const bool fl = nd.lhs == d.out, fr = nd.rhs == d.out;
+        itv nsl, nsr;
+        if (!fl) nsl = slots[nd.lhs];
+        if (!fr) nsr = slots[nd.rhs];
+        const float imm = __uint_as_float(w.y);
+        const itv a = d.form == F_IR ? iv1(imm) : sl;
+        const itv b = d.form == F_RI ? iv1(imm) : sr;
         itv r;
+        bool writes = true;
         if (d.op >= OP_MIN) {
             if (d.op == OP_MEM) {
-                if (d.form == F_RI) slots[d.out] = slots[MEM_BASE + w.y];
-                else slots[MEM_BASE + w.y] = sl;
-                w = nxt;
-                continue;
+                if (d.form == F_RI) r = slots[MEM_BASE + w.y];
+                else { slots[MEM_BASE + w.y] = sl; writes = false; }
+            } else {
+                uint32_t c;
+                r = iv_choice_op(d.op, a, b, c);
+                sink.push(c);
             }
-            uint32_t c;
-            r = iv_choice_op(d.op, a, b, c);
-            sink.push(c);
         } else if (d.op >= OP_ADD) {
             if (d.op == OP_MUL && d.form == F_RI) r = iv_mul_f(sl, imm);
             else r = iv_binary(d.op, a, b);
@@ -91,11 +102,17 @@ __device__ __forceinline__ void run_interval(const uint2* __restrict__ tape, uin
             r = input(w.y);
         } else {  // OP_OUTPUT
             out_fn(w.y, sl);
-            w = nxt;
-            continue;
+            writes = false;
         }
-        slots[d.out] = r;
-        w = nxt;
+        if (writes) {
+            slots[d.out] = r;
+            if (fl) nsl = r;
+            if (fr) nsr = r;
+        } else {
+            if (fl) nsl = slots[nd.lhs];
+            if (fr) nsr = slots[nd.rhs];
+        }
+        w = w1; w1 = w2; d = nd; sl = nsl; sr = nsr;
     }
 }
 
@@ -126,22 +143,28 @@ __device__ __forceinline__ float2 run_f32x2(const uint2* __restrict__ tape, uint
     float2 result = make_float2(nanf_(), nanf_());
     if (n_ops == 0) return result;
     uint2 w = __ldg(tape);
+    uint2 w1 = __ldg(tape + (n_ops > 1 ? 1 : 0));
+    Dec d(w.x);
+    float2 sl = slots[d.lhs], sr = slots[d.rhs];
     for (uint32_t i = 0; i < n_ops; ++i) {
-        uint2 nxt = __ldg(tape + (i + 1 < n_ops ? i + 1 : i));
-        Dec d(w.x);
-        float imm = __uint_as_float(w.y);
-        float2 sl = slots[d.lhs], sr = slots[d.rhs];
-        float2 a = d.form == F_IR ? make_float2(imm, imm) : sl;
-        float2 b = d.form == F_RI ? make_float2(imm, imm) : sr;
+        const uint2 w2 = __ldg(tape + (i + 2 < n_ops ? i + 2 : n_ops - 1));
+        const Dec nd(w1.x);
+        const bool fl = nd.lhs == d.out, fr = nd.rhs == d.out;
+        float2 nsl, nsr;
+        if (!fl) nsl = slots[nd.lhs];
+        if (!fr) nsr = slots[nd.rhs];
+        const float imm = __uint_as_float(w.y);
+        const float2 a = d.form == F_IR ? make_float2(imm, imm) : sl;
+        const float2 b = d.form == F_RI ? make_float2(imm, imm) : sr;
         float2 r;
+        bool writes = true;
         if (d.op >= OP_ADD) {
             if (d.op == OP_MEM) {
-                if (d.form == F_RI) slots[d.out] = slots[MEM_BASE + w.y];
-                else slots[MEM_BASE + w.y] = sl;
-                w = nxt;
-                continue;
+                if (d.form == F_RI) r = slots[MEM_BASE + w.y];
+                else { slots[MEM_BASE + w.y] = sl; writes = false; }
+            } else {
+                r = f32x2_binary(d.op, a, b);
             }
-            r = f32x2_binary(d.op, a, b);
         } else if (d.op >= OP_NEG) {
             r = f32x2_unary(d.op, sl);
         } else if (d.op == OP_COPY) {
@@ -150,11 +173,17 @@ __device__ __forceinline__ float2 run_f32x2(const uint2* __restrict__ tape, uint
             r = input(w.y);
         } else {
             if (w.y == 0) result = sl;
-            w = nxt;
-            continue;
+            writes = false;
         }
-        slots[d.out] = r;
-        w = nxt;
+        if (writes) {
+            slots[d.out] = r;
+            if (fl) nsl = r;
+            if (fr) nsr = r;
+        } else {
+            if (fl) nsl = slots[nd.lhs];
+            if (fr) nsr = slots[nd.rhs];
+        }
+        w = w1; w1 = w2; d = nd; sl = nsl; sr = nsr;
     }
     return result;
 }

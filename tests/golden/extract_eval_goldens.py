@@ -162,3 +162,70 @@ json.dump(tests, open(os.path.join(HERE, "interval_known_answers.json"), "w"), i
 print("interval tests transcribed:", len(tests), "cases:", sum(len(t["cases"]) for t in tests.values()),
       "skipped fns:", skipped)
 print(sorted(tests))
+
+
+# ---------------------------------------------------------------------------
+# grad_slice.rs known answers: `Self::eval_xyz(&tape, &[x], &[y], &[z])[0]` == `Grad::new(v, dx, dy, dz)`
+def parse_grad_tests(path):
+    src = open(path).read()
+    tests, skipped = {}, 0
+    for fn in re.finditer(r"pub fn (test_g_\w+)\(\) \{", src):
+        name = fn.group(1)
+        start = fn.end()
+        depth, i = 1, start
+        while depth and i < len(src):
+            depth += {"{": 1, "}": -1}.get(src[i], 0)
+            i += 1
+        body = src[start:i - 1]
+        line0 = src[:fn.start()].count("\n") + 1
+        nodes, cases, latest = [], [], {}
+        cur_root, ok = None, True
+        for st in split_statements(body):
+            if re.fullmatch(r"let (?:mut )?\w+ = Context::new\(\);", st):
+                continue
+            m = re.fullmatch(r"let (\w+) = ctx\.([xyz])\(\);", st)
+            if m:
+                k = f"{m.group(1)}#{len(nodes)}"; latest[m.group(1)] = k
+                nodes.append([k, "var", [m.group(2)]])
+                continue
+            m = re.fullmatch(r"let (\w+) = ctx\.constant\((%s)\);" % NUM, st)
+            if m:
+                k = f"{m.group(1)}#{len(nodes)}"; latest[m.group(1)] = k
+                nodes.append([k, "const", [num(m.group(2))]])
+                continue
+            m = re.fullmatch(r"let (\w+) = ctx\.(\w+)\((.*)\)\.unwrap\(\);", st)
+            if m:
+                try:
+                    args = [latest[a] if re.fullmatch(r"[A-Za-z_]\w*", a) else num(a)
+                            for a in [x.strip() for x in m.group(3).split(",")]]
+                except (KeyError, ValueError):
+                    ok = False
+                    break
+                k = f"{m.group(1)}#{len(nodes)}"; latest[m.group(1)] = k
+                nodes.append([k, m.group(2), args])
+                continue
+            m = re.fullmatch(r"let (?:shape|s) = F::new\(&ctx, &\[(\w+)\]\)\.unwrap\(\);", st)
+            if m:
+                cur_root = latest.get(m.group(1))
+                continue
+            if re.match(r"let (tape|mut eval|eval) = ", st):
+                continue
+            m = re.fullmatch(r"assert_eq!\(\s*Self::eval_xyz\(&tape, &\[(%s)\], &\[(%s)\], &\[(%s)\]\)\[0\]\s*,\s*"
+                             r"Grad::new\((%s), (%s), (%s), (%s)\)\s*,?\s*\);" % ((NUM,) * 7), st)
+            if m and cur_root:
+                g = [num(v) for v in m.groups()]
+                cases.append({"root": cur_root, "xyz": g[:3], "expect": g[3:]})
+                continue
+            ok = False
+            break
+        if ok and cases:
+            tests[name] = {"source": f"{os.path.relpath(path, REF)}:{line0}", "nodes": nodes, "cases": cases}
+        else:
+            skipped += 1
+    return tests, skipped
+
+
+gtests, gskipped = parse_grad_tests(os.path.join(REF, "fidget-core/src/eval/test/grad_slice.rs"))
+json.dump(gtests, open(os.path.join(HERE, "grad_known_answers.json"), "w"), indent=1)
+print("grad tests transcribed:", len(gtests), "cases:", sum(len(t["cases"]) for t in gtests.values()), "skipped fns:", gskipped)
+print(sorted(gtests))

@@ -184,3 +184,27 @@ def test_interval_contains_point_samples(orc):
             v = t.float_slice_eval(pts)
             ok = np.isnan(v) | ((v >= out[0] - 1e-5 * max(1, abs(out[0]))) & (v <= out[1] + 1e-5 * max(1, abs(out[1]))))
             assert ok.all(), (op, box, out, v[~ok])
+
+
+GRD = json.load(open(os.path.join(GOLD, "grad_known_answers.json")))
+
+
+@pytest.mark.parametrize("name", sorted(GRD))
+def test_grad_known_answers(orc, name):
+    """fidget-core/src/eval/test/grad_slice.rs:54-445 (exact Grad values)."""
+    spec = GRD[name]
+    ctx = orc.Context()
+    env = _build(ctx, spec["nodes"])
+    for case in spec["cases"]:
+        td = ctx.tape(env[case["root"]])
+        t = orc.Tape.from_data(td)
+        vx, vy, vz = td.var_slots()
+        vars_ = [np.zeros((1, 4), dtype=np.float32) for _ in range(max(td.n_vars, 1))]
+        for axis, slot in enumerate((vx, vy, vz)):
+            if slot >= 0:
+                vars_[slot][0, 0] = _f(case["xyz"][axis])
+                vars_[slot][0, 1 + axis] = 1.0
+        out = t.grad_slice_eval(vars_)[0]
+        exp = np.array([_f(v) for v in case["expect"]], dtype=np.float32)
+        assert np.array_equal(out, exp) or (np.isnan(exp).any() and np.array_equal(np.isnan(out), np.isnan(exp))), \
+            (name, case, out)
