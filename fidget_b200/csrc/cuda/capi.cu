@@ -68,6 +68,8 @@ struct fc_ctx {
     int sm_count = 148;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t aux_stream = nullptr;        // fills are painted here, concurrently with the next levels
+    cudaEvent_t ev_fork[MAX_LEVELS] = {}, ev_join = nullptr;
     uint64_t arena_bytes = 1ull << 30;
     // render scratch
     DevBuf arena, jobs[MAX_LEVELS + 1], fills[MAX_LEVELS], choice_scratch, counters, stats, image, heightmap, leaf_tapes;
@@ -298,6 +300,9 @@ int32_t fc_ctx_create(int32_t device, fc_ctx** out) {
                                           std::to_string(prop.major) + std::to_string(prop.minor));
     }
     CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    for (auto& e : c->ev_fork) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     c->stream = c->own_stream;
     *out = c;
     return FC_OK;
@@ -317,6 +322,9 @@ void fc_ctx_destroy(fc_ctx* c) {
     c->heightmap.release();
     c->leaf_tapes.release();
     for (auto ev : c->events) cudaEventDestroy(ev);
+    for (auto e : c->ev_fork) if (e) cudaEventDestroy(e);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    cudaStreamDestroy(c->aux_stream);
     cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -643,6 +651,26 @@ static int32_t bind_vars(const fc_tape* t, const float* values, uint32_t n_value
     return FC_OK;
 }
 
+// Attach the tape's wave schedule to a level-0 launch when the cooperative kernel applies
+// (long tape, few root tiles per SM); returns the grid size or 0.
+static int coop_blocks(fc_ctx* c, const fc_tape* tape, uint64_t n_roots, LevelParams& p) {
+    if (!tape->d_recs || tape->info.n_ops < 64 || env_int("FIDGET_B200_NO_COOP", 0)) return 0;
+    size_t smem = coop_smem_bytes(tape->info.n_ops, tape->info.choice_count);
+    if (smem > 220 * 1024) return 0;
+    // with one lane per tile a warp walks the tape for 32 tiles at once; that only pays when
+    // there are enough root tiles to fill the machine several times over
+    if (n_roots > uint64_t(c->sm_count) * 32 * 24) return 0;
+    p.sched.recs = tape->d_recs;
+    p.sched.wave_start = tape->d_wave_start;
+    p.sched.n_waves = tape->n_waves;
+    p.sched.tail_begin = tape->tail_begin;
+    p.sched.tail_end = tape->tail_end;
+    p.sched.n_segs = uint32_t(tape->segs.size());
+    for (size_t k = 0; k < tape->segs.size(); ++k) p.sched.segs[k] = tape->segs[k];
+    int per_sm = int(std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / (smem + 2048))));
+    return int(std::max<uint64_t>(1, std::min<uint64_t>(n_roots, uint64_t(c->sm_count) * per_sm)));
+}
+
 static cudaEvent_t get_event(fc_ctx* c, size_t i) {
     while (c->events.size() <= i) {
         cudaEvent_t ev;
@@ -675,6 +703,7 @@ int32_t fc_render2d(fc_ctx* c, const fc_tape* tape, const fc_render2d_cfg* cfg, 
     const bool async = (cfg->flags & FC_FLAG_ASYNC) != 0;
     const bool want_stats = stats != nullptr;
     cudaStream_t s = c->stream;
+    const bool serial_fill = env_int("FIDGET_B200_SERIAL_FILL", 0) != 0;
 
     // ---- scratch ----
     const int bps = env_int("FIDGET_B200_BLOCKS_PER_SM", 6);
@@ -745,35 +774,33 @@ int32_t fc_render2d(fc_ctx* c, const fc_tape* tape, const fc_render2d_cfg* cfg, 
             blocks = int(std::min<uint64_t>((warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, uint64_t(grid_blocks)));
         }
         bool coop = false;
-        if (l == 0 && tape->d_recs && tape->info.n_ops >= 64 && !env_int("FIDGET_B200_NO_COOP", 0)) {
-            size_t smem = coop_smem_bytes(tape->info.n_ops, tape->info.choice_count);
-            if (smem <= 220 * 1024) {
-                p.sched.recs = tape->d_recs;
-                p.sched.wave_start = tape->d_wave_start;
-                p.sched.n_waves = tape->n_waves;
-                p.sched.tail_begin = tape->tail_begin;
-                p.sched.tail_end = tape->tail_end;
-                p.sched.n_segs = uint32_t(tape->segs.size());
-                for (size_t k = 0; k < tape->segs.size(); ++k) p.sched.segs[k] = tape->segs[k];
-                int per_sm = int(std::max<size_t>(1, std::min<size_t>(16, (227 * 1024) / (smem + 1024))));
-                int cb = int(std::min<uint64_t>(n_roots, uint64_t(c->sm_count) * per_sm));
-                CU(launch_interval_root_coop_2d(p, std::max(cb, 1), s));
+        if (l == 0) {
+            int cb = coop_blocks(c, tape, n_roots, p);
+            if (cb > 0) {
+                CU(launch_interval_root_coop_2d(p, cb, s));
                 coop = true;
             }
         }
         if (!coop) launch_interval_level_2d(p, std::max(blocks, 1), s);
         ++launches;
         if (timing) CU(cudaEventRecord(get_event(c, ev++), s));
-    }
-    for (int l = 0; l < L; ++l) {
-        FillParams f{};
-        f.tile = ts[l];
-        f.width = cfg->width; f.height = cfg->height;
-        f.fills = c->fills[l].as<FillRec>();
-        f.n_fills = &c->counters.as<Counters>()->n_fills[l];
-        f.out = dimg;
-        launch_fill_2d(f, c->sm_count * 4, s);
-        ++launches;
+        {
+            // the tiles this level proved inside/outside are painted on a second stream while the
+            // next (latency-bound) levels run: fills and leaf pixels never touch the same pixel
+            FillParams f{};
+            f.tile = ts[l];
+            f.width = cfg->width; f.height = cfg->height;
+            f.fills = c->fills[l].as<FillRec>();
+            f.n_fills = &c->counters.as<Counters>()->n_fills[l];
+            f.out = dimg;
+            cudaStream_t fs = serial_fill ? s : c->aux_stream;
+            if (!serial_fill) {
+                CU(cudaEventRecord(c->ev_fork[l], s));
+                CU(cudaStreamWaitEvent(c->aux_stream, c->ev_fork[l], 0));
+            }
+            launch_fill_2d(f, c->sm_count * 2, fs);
+            ++launches;
+        }
     }
     if (timing) CU(cudaEventRecord(get_event(c, ev++), s));
     {
@@ -791,6 +818,10 @@ int32_t fc_render2d(fc_ctx* c, const fc_tape* tape, const fc_render2d_cfg* cfg, 
         q.vb = vb;
         launch_pixels_2d(q, c->sm_count * env_int("FIDGET_B200_PIXEL_BLOCKS_PER_SM", 8), s);
         ++launches;
+    }
+    if (!serial_fill) {
+        CU(cudaEventRecord(c->ev_join, c->aux_stream));
+        CU(cudaStreamWaitEvent(s, c->ev_join, 0));
     }
     if (timing) CU(cudaEventRecord(get_event(c, ev++), s));
     CU(cudaGetLastError());
@@ -923,7 +954,15 @@ int32_t fc_render3d(fc_ctx* c, const fc_tape* tape, const fc_render3d_cfg* cfg, 
             uint64_t warps = (n_roots + 31) / 32;
             blocks = int(std::min<uint64_t>((warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, uint64_t(grid_blocks)));
         }
-        launch_interval_level_3d(p, std::max(blocks, 1), s);
+        bool coop = false;
+        if (l == 0) {
+            int cb = coop_blocks(c, tape, n_roots, p);
+            if (cb > 0) {
+                CU(launch_interval_root_coop_3d(p, cb, s));
+                coop = true;
+            }
+        }
+        if (!coop) launch_interval_level_3d(p, std::max(blocks, 1), s);
         ++launches;
         if (timing) CU(cudaEventRecord(get_event(c, ev++), s));
     }

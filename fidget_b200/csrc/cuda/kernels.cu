@@ -58,39 +58,29 @@ struct Dec {
 // Interval interpreter.  `Input` maps a variable index to an interval,
 // `Sink` receives one choice per choice clause in evaluation order, `Out`
 // receives (output index, value).
-// The loop is software-pipelined: while clause i executes, clause i+1 is already
-// decoded and its operands are being loaded from the register file (local
-// memory); an operand that is the result of clause i is forwarded in registers
-// instead of taking the store -> load round trip.
 template <class Input, class Sink, class Out>
 __device__ __forceinline__ void run_interval(const uint2* __restrict__ tape, uint32_t n_ops, itv* slots,
                                              Input input, Sink& sink, Out out_fn) {
     if (n_ops == 0) return;
     uint2 w = __ldg(tape);
-    uint2 w1 = __ldg(tape + (n_ops > 1 ? 1 : 0));
-    Dec d(w.x);
-    itv sl = slots[d.lhs], sr = slots[d.rhs];
     for (uint32_t i = 0; i < n_ops; ++i) {
-        const uint2 w2 = __ldg(tape + (i + 2 < n_ops ? i + 2 : n_ops - 1));
-        const Dec nd(w1.x);
-        const bool fl = nd.lhs == d.out, fr = nd.rhs == d.out;
-        itv nsl, nsr;
-        if (!fl) nsl = slots[nd.lhs];
-        if (!fr) nsr = slots[nd.rhs];
-        const float imm = __uint_as_float(w.y);
-        const itv a = d.form == F_IR ? iv1(imm) : sl;
-        const itv b = d.form == F_RI ? iv1(imm) : sr;
+        uint2 nxt = __ldg(tape + (i + 1 < n_ops ? i + 1 : i));
+        Dec d(w.x);
+        float imm = __uint_as_float(w.y);
+        itv sl = slots[d.lhs], sr = slots[d.rhs];
+        itv a = d.form == F_IR ? iv1(imm) : sl;
+        itv b = d.form == F_RI ? iv1(imm) : sr;
         itv r;
-        bool writes = true;
         if (d.op >= OP_MIN) {
             if (d.op == OP_MEM) {
-                if (d.form == F_RI) r = slots[MEM_BASE + w.y];
-                else { slots[MEM_BASE + w.y] = sl; writes = false; }
-            } else {
-                uint32_t c;
-                r = iv_choice_op(d.op, a, b, c);
-                sink.push(c);
+                if (d.form == F_RI) slots[d.out] = slots[MEM_BASE + w.y];
+                else slots[MEM_BASE + w.y] = sl;
+                w = nxt;
+                continue;
             }
+            uint32_t c;
+            r = iv_choice_op(d.op, a, b, c);
+            sink.push(c);
         } else if (d.op >= OP_ADD) {
             if (d.op == OP_MUL && d.form == F_RI) r = iv_mul_f(sl, imm);
             else r = iv_binary(d.op, a, b);
@@ -102,17 +92,11 @@ __device__ __forceinline__ void run_interval(const uint2* __restrict__ tape, uin
             r = input(w.y);
         } else {  // OP_OUTPUT
             out_fn(w.y, sl);
-            writes = false;
+            w = nxt;
+            continue;
         }
-        if (writes) {
-            slots[d.out] = r;
-            if (fl) nsl = r;
-            if (fr) nsr = r;
-        } else {
-            if (fl) nsl = slots[nd.lhs];
-            if (fr) nsr = slots[nd.rhs];
-        }
-        w = w1; w1 = w2; d = nd; sl = nsl; sr = nsr;
+        slots[d.out] = r;
+        w = nxt;
     }
 }
 
@@ -143,28 +127,22 @@ __device__ __forceinline__ float2 run_f32x2(const uint2* __restrict__ tape, uint
     float2 result = make_float2(nanf_(), nanf_());
     if (n_ops == 0) return result;
     uint2 w = __ldg(tape);
-    uint2 w1 = __ldg(tape + (n_ops > 1 ? 1 : 0));
-    Dec d(w.x);
-    float2 sl = slots[d.lhs], sr = slots[d.rhs];
     for (uint32_t i = 0; i < n_ops; ++i) {
-        const uint2 w2 = __ldg(tape + (i + 2 < n_ops ? i + 2 : n_ops - 1));
-        const Dec nd(w1.x);
-        const bool fl = nd.lhs == d.out, fr = nd.rhs == d.out;
-        float2 nsl, nsr;
-        if (!fl) nsl = slots[nd.lhs];
-        if (!fr) nsr = slots[nd.rhs];
-        const float imm = __uint_as_float(w.y);
-        const float2 a = d.form == F_IR ? make_float2(imm, imm) : sl;
-        const float2 b = d.form == F_RI ? make_float2(imm, imm) : sr;
+        uint2 nxt = __ldg(tape + (i + 1 < n_ops ? i + 1 : i));
+        Dec d(w.x);
+        float imm = __uint_as_float(w.y);
+        float2 sl = slots[d.lhs], sr = slots[d.rhs];
+        float2 a = d.form == F_IR ? make_float2(imm, imm) : sl;
+        float2 b = d.form == F_RI ? make_float2(imm, imm) : sr;
         float2 r;
-        bool writes = true;
         if (d.op >= OP_ADD) {
             if (d.op == OP_MEM) {
-                if (d.form == F_RI) r = slots[MEM_BASE + w.y];
-                else { slots[MEM_BASE + w.y] = sl; writes = false; }
-            } else {
-                r = f32x2_binary(d.op, a, b);
+                if (d.form == F_RI) slots[d.out] = slots[MEM_BASE + w.y];
+                else slots[MEM_BASE + w.y] = sl;
+                w = nxt;
+                continue;
             }
+            r = f32x2_binary(d.op, a, b);
         } else if (d.op >= OP_NEG) {
             r = f32x2_unary(d.op, sl);
         } else if (d.op == OP_COPY) {
@@ -173,17 +151,11 @@ __device__ __forceinline__ float2 run_f32x2(const uint2* __restrict__ tape, uint
             r = input(w.y);
         } else {
             if (w.y == 0) result = sl;
-            writes = false;
+            w = nxt;
+            continue;
         }
-        if (writes) {
-            slots[d.out] = r;
-            if (fl) nsl = r;
-            if (fr) nsr = r;
-        } else {
-            if (fl) nsl = slots[nd.lhs];
-            if (fr) nsr = slots[nd.rhs];
-        }
-        w = w1; w1 = w2; d = nd; sl = nsl; sr = nsr;
+        slots[d.out] = r;
+        w = nxt;
     }
     return result;
 }
@@ -943,8 +915,9 @@ __device__ __forceinline__ Rec load_rec(const CoopRec* recs, uint32_t i) {
     return Rec(__ldg(reinterpret_cast<const uint4*>(recs) + i));
 }
 
+template <int DIM>
 __global__ void __launch_bounds__(COOP_THREADS)
-k_interval_root_coop_2d(const __grid_constant__ LevelParams p) {
+k_interval_root_coop(const __grid_constant__ LevelParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t n = p.root_tape.n_ops, nch = p.root_tape.n_choices;
     const uint32_t cw = (nch + 15u) / 16u + 1u;
@@ -961,7 +934,7 @@ k_interval_root_coop_2d(const __grid_constant__ LevelParams p) {
     const uint32_t tid = threadIdx.x, T = p.tile;
     const CoopRec* __restrict__ recs = p.sched.recs;
     const uint32_t* __restrict__ ws = p.sched.wave_start;
-    const uint32_t n_roots = p.roots_x * p.roots_y;
+    const uint32_t n_roots = p.roots_x * p.roots_y * (DIM == 3 ? p.roots_z : 1u);
     const uint2* __restrict__ tape = p.root_tape.ptr;
 
     for (;;) {
@@ -976,10 +949,11 @@ k_interval_root_coop_2d(const __grid_constant__ LevelParams p) {
         __syncthreads();
         const uint32_t tile = s_tile;
         if (tile >= n_roots) break;
-        const uint32_t cx = p.root_x0 + (tile % p.roots_x) * T, cy = p.root_y0 + (tile / p.roots_x) * T;
+        const uint32_t cx = p.root_x0 + (tile % p.roots_x) * T, cy = p.root_y0 + ((tile / p.roots_x) % p.roots_y) * T;
+        const uint32_t cz = DIM == 3 ? p.root_z0 + (tile / (p.roots_x * p.roots_y)) * T : 0u;
         itv vx, vy, vz;
-        xform_iv(p.mat, iv(float(cx), float(cx) + float(T)), iv(float(cy), float(cy) + float(T)), iv(p.z2d, p.z2d),
-                 vx, vy, vz);
+        xform_iv(p.mat, iv(float(cx), float(cx) + float(T)), iv(float(cy), float(cy) + float(T)),
+                 DIM == 3 ? iv(float(cz), float(cz) + float(T)) : iv(p.z2d, p.z2d), vx, vy, vz);
         auto put_choice = [&](uint32_t cidx, uint32_t c) {
             atomicOr(&chs[cidx >> 4], c << ((cidx & 15u) * 2u));
             if (c != 3u) s_nonboth = 1u;
@@ -1082,17 +1056,38 @@ k_interval_root_coop_2d(const __grid_constant__ LevelParams p) {
                         prev = rc.p;
                     }
                 }
-                s_agg_lo[tid] = alo; s_agg_hi[tid] = ahi; s_agg_f[tid] = uint8_t(af);
+                // exclusive block scan of the per-thread aggregates (warp shuffles + one smem hop)
+                float xlo = alo, xhi = ahi;
+                uint32_t xf = af;
+                const uint32_t ln = tid & 31u, wp = tid >> 5;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float vlo = __shfl_up_sync(FULL, xlo, o), vhi = __shfl_up_sync(FULL, xhi, o);
+                    const uint32_t vf = __shfl_up_sync(FULL, xf, o);
+                    if (ln >= uint32_t(o)) {
+                        xlo = is_min ? fminf(vlo, xlo) : fmaxf(vlo, xlo);
+                        xhi = is_min ? fminf(vhi, xhi) : fmaxf(vhi, xhi);
+                        xf |= vf;
+                    }
+                }
+                if (ln == 31u) { s_agg_lo[wp] = xlo; s_agg_hi[wp] = xhi; s_agg_f[wp] = uint8_t(xf); }
+                // exclusive within the warp
+                float elo = __shfl_up_sync(FULL, xlo, 1), ehi = __shfl_up_sync(FULL, xhi, 1);
+                uint32_t ef = __shfl_up_sync(FULL, xf, 1);
+                if (ln == 0u) { elo = ident; ehi = ident; ef = 0; }
                 __syncthreads();
                 if (c0 < c1) {
                     const itv start = vals[prev_first];
                     float lo = start.x, hi = start.y;
                     uint32_t f = uint32_t(iv_has_nan(start));
-                    for (uint32_t k = 0; k < tid; ++k) {
+                    for (uint32_t k = 0; k < wp; ++k) {
                         f |= s_agg_f[k];
                         lo = is_min ? fminf(lo, s_agg_lo[k]) : fmaxf(lo, s_agg_lo[k]);
                         hi = is_min ? fminf(hi, s_agg_hi[k]) : fmaxf(hi, s_agg_hi[k]);
                     }
+                    f |= ef;
+                    lo = is_min ? fminf(lo, elo) : fmaxf(lo, elo);
+                    hi = is_min ? fminf(hi, ehi) : fmaxf(hi, ehi);
                     uint32_t prev = c0 > b ? load_rec(recs, c0 - 1).p : prev_first;
                     for (uint32_t i = c0; i < c1; ++i) {
                         const Rec rc = load_rec(recs, i);
@@ -1116,8 +1111,15 @@ k_interval_root_coop_2d(const __grid_constant__ LevelParams p) {
         const bool fill_in = !p.pixel_perfect && r.y < 0.0f;
         const bool fill_out = !p.pixel_perfect && !fill_in && r.x > 0.0f;
         const bool amb = !fill_in && !fill_out;
+        if (DIM == 3 && fill_in) {   // voxel.rs:310-317
+            const unsigned long long key = (unsigned long long)(cz + T + 1u) << 32;
+            for (uint32_t q = tid; q < T * T; q += COOP_THREADS) {
+                const uint32_t x = cx + q % T, y = cy + q / T;
+                if (x < p.width && y < p.height) atomicMax(&p.heightmap[size_t(y) * p.width + x], key);
+            }
+        }
         if (tid == 0) {
-            if (!amb) {
+            if (DIM == 2 && !amb) {
                 uint32_t slot = atomicAdd(&p.ctr->n_fills[0], 1u);
                 if (slot < p.cap_fills) {
                     FillRec fr;
@@ -1178,12 +1180,23 @@ k_interval_root_coop_2d(const __grid_constant__ LevelParams p) {
                         O = up & (ext | O);
                         U = up & U;
                     }
-                    s_agg_f[tid] = uint8_t(O);
-                    s_agg_u[tid] = uint8_t(U);
+                    // inclusive suffix scan of F = (O, U) under composition (earlier o later)
+                    uint32_t xO = O, xU = U;
+                    const uint32_t ln = tid & 31u, wp = tid >> 5;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t vO = __shfl_down_sync(FULL, xO, o), vU = __shfl_down_sync(FULL, xU, o);
+                        if (ln + uint32_t(o) < 32u) { xO = xO | (xU & vO); xU = xU & vU; }
+                    }
+                    if (ln == 0u) { s_agg_f[wp] = uint8_t(xO); s_agg_u[wp] = uint8_t(xU); }
+                    // composition of the chunks AFTER this thread inside the warp
+                    uint32_t eO = __shfl_down_sync(FULL, xO, 1), eU = __shfl_down_sync(FULL, xU, 1);
+                    if (ln == 31u) { eO = 0; eU = 1; }
                     __syncthreads();
                     if (c0 < c1) {
                         uint32_t y = 0;   // (uses_prev & live) of the element right after this chunk
-                        for (uint32_t k = COOP_THREADS - 1; k > tid; --k) y = s_agg_f[k] | (s_agg_u[k] & y);
+                        for (uint32_t k = COOP_THREADS / 32; k > wp + 1u; --k) y = s_agg_f[k - 1] | (s_agg_u[k - 1] & y);
+                        y = eO | (eU & y);
                         for (uint32_t i = c1; i > c0; --i) {
                             const Rec rc = load_rec(recs, i - 1);
                             const uint32_t prevp = i - 1 > b ? load_rec(recs, i - 2).p : prev_first;
@@ -1300,7 +1313,7 @@ k_interval_root_coop_2d(const __grid_constant__ LevelParams p) {
                 TileJob o;
                 o.x = cx;
                 o.y = cy;
-                o.z = 0;
+                o.z = cz;
                 o.pad = 0;
                 o.tape = child;
                 p.jobs_out[slot] = o;
@@ -1310,17 +1323,20 @@ k_interval_root_coop_2d(const __grid_constant__ LevelParams p) {
     }
 }
 
-cudaError_t launch_interval_root_coop_2d(const LevelParams& p, int blocks, cudaStream_t s) {
+template <int DIM>
+static cudaError_t launch_coop(const LevelParams& p, int blocks, cudaStream_t s) {
     size_t smem = coop_smem_bytes(p.root_tape.n_ops, p.root_tape.n_choices);
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_interval_root_coop_2d, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        cudaError_t e = cudaFuncSetAttribute(k_interval_root_coop<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    k_interval_root_coop_2d<<<blocks, COOP_THREADS, smem, s>>>(p);
+    k_interval_root_coop<DIM><<<blocks, COOP_THREADS, smem, s>>>(p);
     return cudaGetLastError();
 }
+cudaError_t launch_interval_root_coop_2d(const LevelParams& p, int blocks, cudaStream_t s) { return launch_coop<2>(p, blocks, s); }
+cudaError_t launch_interval_root_coop_3d(const LevelParams& p, int blocks, cudaStream_t s) { return launch_coop<3>(p, blocks, s); }
 
 }  // namespace fdev
 

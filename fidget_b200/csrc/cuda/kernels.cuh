@@ -205,6 +205,7 @@ void launch_merge_slabs(const void* const* d_slabs, uint32_t n_slabs, uint32_t n
 void launch_interval_level_2d(const LevelParams& p, int blocks, cudaStream_t s);
 size_t coop_smem_bytes(uint32_t n_ops, uint32_t n_choices);
 cudaError_t launch_interval_root_coop_2d(const LevelParams& p, int blocks, cudaStream_t s);
+cudaError_t launch_interval_root_coop_3d(const LevelParams& p, int blocks, cudaStream_t s);
 void launch_pixels_2d(const PixelParams& p, int blocks, cudaStream_t s);
 void launch_fill_2d(const FillParams& p, int blocks, cudaStream_t s);
 

@@ -208,3 +208,81 @@ def test_grad_known_answers(orc, name):
         exp = np.array([_f(v) for v in case["expect"]], dtype=np.float32)
         assert np.array_equal(out, exp) or (np.isnan(exp).any() and np.array_equal(np.isnan(out), np.isnan(exp))), \
             (name, case, out)
+
+
+def _test_args():
+    # eval/test/mod.rs:48-63 (test_args)
+    a = [np.float32(np.pi) * np.float32(2.0) * np.float32(i) / np.float32(32) for i in range(-32, 33)]
+    a += [1.0, 5.0, 0.5, 1.5, 10.0, np.pi, np.pi / 2, 1 / np.pi, np.sqrt(2.0), np.nan]
+    return np.array(a, dtype=np.float32)
+
+
+def _canon(op, a, b=None):
+    """Canonical f32 definitions of eval/test/mod.rs:188-246, evaluated with numpy float32
+    (only the operations IEEE-754 fixes bit for bit are listed)."""
+    f = np.float32
+    with np.errstate(all="ignore"):
+        if op == "neg": return -a
+        if op == "abs": return np.abs(a)
+        if op == "recip": return f(1.0) / a
+        if op == "sqrt": return np.sqrt(a)
+        if op == "square": return a * a
+        if op == "floor": return np.floor(a)
+        if op == "ceil": return np.ceil(a)
+        if op == "round": return np.where(np.isnan(a), a, np.copysign(np.floor(np.abs(a) + f(0.5)), a)).astype(f)
+        if op == "not": return (a == 0).astype(f)
+        if op == "add": return a + b
+        if op == "sub": return a - b
+        if op == "mul": return a * b
+        if op == "div": return a / b
+        if op == "min": return np.where(np.isnan(a) | np.isnan(b), f(np.nan), np.where(a < b, a, b))
+        if op == "max": return np.where(np.isnan(a) | np.isnan(b), f(np.nan), np.where(a > b, a, b))
+        if op == "compare": return np.where(np.isnan(a) | np.isnan(b), f(np.nan),
+                                            np.where(a < b, f(-1), np.where(a > b, f(1), f(0))))
+        if op == "and": return np.where(a == 0, a, b)
+        if op == "or": return np.where(a != 0, a, b)
+        if op == "mod":
+            r = np.fmod(a, b)
+            return np.where(r < 0, r + np.abs(b), r)
+    raise KeyError(op)
+
+
+@pytest.mark.parametrize("op", ["neg", "abs", "recip", "sqrt", "square", "floor", "ceil", "round", "not"])
+def test_float_slice_unary_canonical(orc, op):
+    # eval/test/float_slice.rs:391-432: every op equals its canonical f32 definition exactly
+    ctx = orc.Context()
+    t = orc.Tape.from_data(ctx.tape(ctx.unary(op, ctx.x())))
+    a = _test_args()
+    got, want = t.float_slice_eval([a]), _canon(op, a).astype(np.float32)
+    assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(got[~np.isnan(got)], want[~np.isnan(want)])
+
+
+@pytest.mark.parametrize("op", ["add", "sub", "mul", "div", "min", "max", "compare", "and", "or", "mod"])
+def test_float_slice_binary_canonical(orc, op):
+    args = _test_args()
+    a, b = [g.ravel().astype(np.float32) for g in np.meshgrid(args, args)]
+    # reg-reg, reg-imm and imm-reg forms (float_slice.rs:434-560)
+    ctx = orc.Context()
+    x, y = ctx.x(), ctx.y()
+    td = ctx.tape(ctx.binary(op, x, y))
+    t = orc.Tape.from_data(td)
+    vx, vy, _ = td.var_slots()
+    vars_ = [None, None]
+    vars_[vx], vars_[vy] = a, b
+    got, want = t.float_slice_eval(vars_), _canon(op, a, b).astype(np.float32)
+    assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(got[~np.isnan(got)], want[~np.isnan(want)])
+    for k in args[::7]:
+        if np.isnan(k):
+            continue
+        for imm_first in (False, True):
+            ctx = orc.Context()
+            x = ctx.x()
+            node = ctx.binary(op, float(k), x) if imm_first else ctx.binary(op, x, float(k))
+            t = orc.Tape.from_data(ctx.tape(node))
+            if t.n_vars == 0:
+                continue                     # folded to a constant
+            got = t.float_slice_eval([args])
+            kk = np.full_like(args, k)
+            want = (_canon(op, kk, args) if imm_first else _canon(op, args, kk)).astype(np.float32)
+            assert np.array_equal(np.isnan(got), np.isnan(want)) and \
+                np.array_equal(got[~np.isnan(got)], want[~np.isnan(want)]), (op, k, imm_first)
