@@ -180,11 +180,14 @@ def main():
     gathered = torch.empty_like(image) if world > 1 else None
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    from fidget_b200.shard import render2d_bands
+    full_cfg = fb.RenderConfig2D(SIZE, SIZE)
+
     def step():
-        fb.render2d(shape, cfg, out=image, asynchronous=True)
         if world > 1:
-            band = image[rows[0] * T0: rows[1] * T0]
-            dist.all_gather_into_tensor(gathered, band)
+            render2d_bands(shape, full_cfg, image, gathered)   # band render + ONE all-gather
+        else:
+            fb.render2d(shape, cfg, out=image, asynchronous=True)
 
     def sync_all():
         if world > 1:

@@ -1,6 +1,7 @@
 // Host orchestration + C ABI of libfidget_cuda (include/fidget_cuda.h).
 #include <algorithm>
 #include <atomic>
+#include <memory>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -56,6 +57,21 @@ bool is_device_ptr(const void* p) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// Pinned (page-locked, mapped) host memory can be written by kernels directly over PCIe.
+// Measured on B200 (profiles/r01_prospero4096.md): SM stores over PCIe reach well under half the
+// bandwidth of a DMA copy (3.07 ms vs 2.07 ms end to end for a 67 MB image), so this is opt-in
+// (FIDGET_B200_ZEROCOPY=1); the default stages the image in HBM and copies it with the DMA engine.
+// Returns the device alias of `p` or null.
+void* pinned_device_alias(const void* p) {
+    if (!p) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+
 int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return v && *v ? atoi(v) : dflt;
@@ -72,9 +88,11 @@ struct fc_ctx {
     cudaEvent_t ev_fork[MAX_LEVELS] = {}, ev_join = nullptr;
     uint64_t arena_bytes = 1ull << 30;
     // render scratch
-    DevBuf arena, jobs[MAX_LEVELS + 1], fills[MAX_LEVELS], choice_scratch, counters, stats, image, heightmap, leaf_tapes;
+    DevBuf arena, jobs[MAX_LEVELS + 1], fills[MAX_LEVELS], choice_scratch, counters, stats, image, heightmap, leaf_tapes, zsort;
     std::vector<cudaEvent_t> events;
     std::mutex mu;
+    std::shared_ptr<struct Sched> sched_cache[4];
+    unsigned sched_next = 0;
 };
 
 struct fc_tape {
@@ -84,11 +102,25 @@ struct fc_tape {
     std::vector<uint2> host;  // copy of the device clauses
     fc_tape_info info{};
     int ax[3] = {-1, -1, -1};  // input slots of X, Y, Z
-    // cooperative level-0 schedule (empty when the tape is unsuitable)
+    // cooperative level-0 schedule (null when the tape is unsuitable); shared between tapes
+    // created from identical bytecode (re-uploading an unchanged shape every frame is the
+    // common interactive pattern)
+    std::shared_ptr<struct Sched> sched;
+};
+
+struct Sched {
+    int device = 0;
+    uint64_t hash = 0;
+    size_t n_clauses = 0;
     CoopRec* d_recs = nullptr;
     uint32_t* d_wave_start = nullptr;
     uint32_t n_waves = 0, tail_begin = 0, tail_end = 0;
     std::vector<CoopSeg> segs;
+    ~Sched() {
+        cudaSetDevice(device);
+        if (d_recs) cudaFree(d_recs);
+        if (d_wave_start) cudaFree(d_wave_start);
+    }
 };
 
 // Dependency-wave schedule of a register tape: value id = position of the
@@ -183,20 +215,40 @@ static bool build_schedule(const std::vector<uint2>& cl, std::vector<CoopRec>& r
     return segs.size() <= size_t(COOP_MAX_SEGS);
 }
 
+static uint64_t fnv1a(const void* data, size_t n) {
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+
 static void upload_schedule(fc_tape* t) {
+    fc_ctx* c = t->ctx;
+    if (t->host.size() < 64) return;   // the cooperative kernel is never used for short tapes
+    const uint64_t h = fnv1a(t->host.data(), t->host.size() * sizeof(uint2));
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        for (auto& sp : c->sched_cache)
+            if (sp && sp->hash == h && sp->n_clauses == t->host.size()) { t->sched = sp; return; }
+    }
     std::vector<CoopRec> recs;
     std::vector<uint32_t> ws;
     uint32_t tb = 0;
-    if (!build_schedule(t->host, recs, ws, tb, t->segs)) return;
-    if (cudaMalloc(&t->d_recs, recs.size() * sizeof(CoopRec)) != cudaSuccess) { t->d_recs = nullptr; cudaGetLastError(); return; }
-    if (cudaMalloc(&t->d_wave_start, ws.size() * 4) != cudaSuccess) {
-        cudaFree(t->d_recs); t->d_recs = nullptr; cudaGetLastError(); return;
-    }
-    cudaMemcpy(t->d_recs, recs.data(), recs.size() * sizeof(CoopRec), cudaMemcpyHostToDevice);
-    cudaMemcpy(t->d_wave_start, ws.data(), ws.size() * 4, cudaMemcpyHostToDevice);
-    t->n_waves = uint32_t(ws.size() - 1);
-    t->tail_begin = tb;
-    t->tail_end = uint32_t(recs.size());
+    auto sc = std::make_shared<Sched>();
+    sc->device = c->device;
+    sc->hash = h;
+    sc->n_clauses = t->host.size();
+    if (!build_schedule(t->host, recs, ws, tb, sc->segs)) return;
+    if (cudaMalloc(&sc->d_recs, recs.size() * sizeof(CoopRec)) != cudaSuccess) { sc->d_recs = nullptr; cudaGetLastError(); return; }
+    if (cudaMalloc(&sc->d_wave_start, ws.size() * 4) != cudaSuccess) { sc->d_wave_start = nullptr; cudaGetLastError(); return; }
+    cudaMemcpy(sc->d_recs, recs.data(), recs.size() * sizeof(CoopRec), cudaMemcpyHostToDevice);
+    cudaMemcpy(sc->d_wave_start, ws.data(), ws.size() * 4, cudaMemcpyHostToDevice);
+    sc->n_waves = uint32_t(ws.size() - 1);
+    sc->tail_begin = tb;
+    sc->tail_end = uint32_t(recs.size());
+    t->sched = sc;
+    std::lock_guard<std::mutex> g(c->mu);
+    c->sched_cache[c->sched_next++ % 4] = sc;
 }
 
 struct fc_eval {
@@ -321,6 +373,7 @@ void fc_ctx_destroy(fc_ctx* c) {
     c->image.release();
     c->heightmap.release();
     c->leaf_tapes.release();
+    c->zsort.release();
     for (auto ev : c->events) cudaEventDestroy(ev);
     for (auto e : c->ev_fork) if (e) cudaEventDestroy(e);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -404,8 +457,6 @@ int32_t fc_tape_release(fc_tape* t) {
     if (t->refs.fetch_sub(1) == 1) {
         cudaSetDevice(t->ctx->device);
         cudaFree(t->dev);
-        if (t->d_recs) cudaFree(t->d_recs);
-        if (t->d_wave_start) cudaFree(t->d_wave_start);
         delete t;
     }
     return FC_OK;
@@ -654,19 +705,20 @@ static int32_t bind_vars(const fc_tape* t, const float* values, uint32_t n_value
 // Attach the tape's wave schedule to a level-0 launch when the cooperative kernel applies
 // (long tape, few root tiles per SM); returns the grid size or 0.
 static int coop_blocks(fc_ctx* c, const fc_tape* tape, uint64_t n_roots, LevelParams& p) {
-    if (!tape->d_recs || tape->info.n_ops < 64 || env_int("FIDGET_B200_NO_COOP", 0)) return 0;
+    const Sched* sc = tape->sched.get();
+    if (!sc || !sc->d_recs || !sc->d_wave_start || env_int("FIDGET_B200_NO_COOP", 0)) return 0;
     size_t smem = coop_smem_bytes(tape->info.n_ops, tape->info.choice_count);
     if (smem > 220 * 1024) return 0;
     // with one lane per tile a warp walks the tape for 32 tiles at once; that only pays when
     // there are enough root tiles to fill the machine several times over
     if (n_roots > uint64_t(c->sm_count) * 32 * 24) return 0;
-    p.sched.recs = tape->d_recs;
-    p.sched.wave_start = tape->d_wave_start;
-    p.sched.n_waves = tape->n_waves;
-    p.sched.tail_begin = tape->tail_begin;
-    p.sched.tail_end = tape->tail_end;
-    p.sched.n_segs = uint32_t(tape->segs.size());
-    for (size_t k = 0; k < tape->segs.size(); ++k) p.sched.segs[k] = tape->segs[k];
+    p.sched.recs = sc->d_recs;
+    p.sched.wave_start = sc->d_wave_start;
+    p.sched.n_waves = sc->n_waves;
+    p.sched.tail_begin = sc->tail_begin;
+    p.sched.tail_end = sc->tail_end;
+    p.sched.n_segs = uint32_t(sc->segs.size());
+    for (size_t k = 0; k < sc->segs.size(); ++k) p.sched.segs[k] = sc->segs[k];
     int per_sm = int(std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / (smem + 2048))));
     return int(std::max<uint64_t>(1, std::min<uint64_t>(n_roots, uint64_t(c->sm_count) * per_sm)));
 }
@@ -722,12 +774,18 @@ int32_t fc_render2d(fc_ctx* c, const fc_tape* tape, const fc_render2d_cfg* cfg, 
         CU(c->jobs[l].ensure(level_tiles[l] * sizeof(TileJob)));
         CU(c->fills[l - 1].ensure(level_tiles[l] * sizeof(FillRec)));
     }
-    const bool out_dev = is_device_ptr(out);
+    bool out_dev = is_device_ptr(out);
     float* dimg = out;
     const size_t img_bytes = size_t(cfg->width) * cfg->height * 4;
     if (!out_dev) {
-        CU(c->image.ensure(img_bytes));
-        dimg = c->image.as<float>();
+        void* alias = env_int("FIDGET_B200_ZEROCOPY", 0) ? pinned_device_alias(out) : nullptr;
+        if (alias) {
+            dimg = static_cast<float*>(alias);   // zero-copy: kernels store straight into the host image
+            out_dev = true;
+        } else {
+            CU(c->image.ensure(img_bytes));
+            dimg = c->image.as<float>();
+        }
     }
     CU(cudaMemsetAsync(c->counters.p, 0, sizeof(Counters), s));
     if (want_stats) CU(cudaMemsetAsync(c->stats.p, 0, sizeof(Stats), s));
@@ -906,11 +964,17 @@ int32_t fc_render3d(fc_ctx* c, const fc_tape* tape, const fc_render3d_cfg* cfg, 
     }
     const size_t npix = size_t(cfg->width) * cfg->height;
     CU(c->heightmap.ensure(npix * 8));
-    const bool out_dev = is_device_ptr(out);
+    bool out_dev = is_device_ptr(out);
     void* dimg = out;
     if (!out_dev) {
-        CU(c->image.ensure(npix * 16));
-        dimg = c->image.p;
+        void* alias = env_int("FIDGET_B200_ZEROCOPY", 0) ? pinned_device_alias(out) : nullptr;
+        if (alias) {
+            dimg = alias;
+            out_dev = true;
+        } else {
+            CU(c->image.ensure(npix * 16));
+            dimg = c->image.p;
+        }
     }
     CU(cudaMemsetAsync(c->counters.p, 0, sizeof(Counters), s));
     CU(cudaMemsetAsync(c->heightmap.p, 0, npix * 8, s));
@@ -969,6 +1033,16 @@ int32_t fc_render3d(fc_ctx* c, const fc_tape* tape, const fc_render3d_cfg* cfg, 
     {
         VoxelParams q{};
         q.tile = ts[L - 1];
+        if (!env_int("FIDGET_B200_NO_ZSORT", 0)) {
+            const uint32_t n_layers = (roots_z * T0) / ts[L - 1];
+            CU(c->zsort.ensure(size_t(n_layers + 1) * 4 + level_cap[L] * 4));
+            uint32_t* hist = c->zsort.as<uint32_t>();
+            uint32_t* order = hist + n_layers + 1;
+            launch_leaf_zsort(c->jobs[L].as<TileJob>(), &c->counters.as<Counters>()->n_jobs[L], uint32_t(level_cap[L]),
+                              z_begin, ts[L - 1], n_layers, hist, order, s);
+            launches += 3;
+            q.order = order;
+        }
         q.width = cfg->width; q.height = cfg->height;
         memcpy(q.mat.m, cfg->mat, sizeof q.mat.m);
         q.jobs = c->jobs[L].as<TileJob>();

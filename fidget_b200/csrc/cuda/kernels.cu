@@ -494,6 +494,7 @@ __global__ void __launch_bounds__(128) k_voxels_3d(const __grid_constant__ Voxel
         if (lane == 0) j = atomicAdd(&p.ctr->cursor[p.cursor], 1u);
         j = __shfl_sync(FULL, j, 0);
         if (j >= n_jobs) break;
+        if (p.order) j = p.order[j];   // front-to-back: tiles behind a finished column find it done and exit early
         const TileJob* job = p.jobs + j;
         const uint32_t cx = job->x, cy = job->y, cz = job->z;
         const TapeRef tr = job->tape;
@@ -537,6 +538,40 @@ __global__ void __launch_bounds__(128) k_voxels_3d(const __grid_constant__ Voxel
     }
 }
 void launch_voxels_3d(const VoxelParams& p, int blocks, cudaStream_t s) { k_voxels_3d<<<blocks, 128, 0, s>>>(p); }
+
+// Front-to-back ordering of the leaf tiles (the reference walks Z descending, voxel.rs:244-263,
+// 335-351): a counting sort by Z layer, front layer first.
+__global__ void k_zsort_hist(const TileJob* jobs, const uint32_t* n_jobs, uint32_t cap, uint32_t z0, uint32_t tile,
+                             uint32_t n_layers, uint32_t* hist) {
+    const uint32_t n = min(*n_jobs, cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t layer = min((jobs[i].z - z0) / tile, n_layers - 1u);
+        atomicAdd(&hist[n_layers - 1u - layer], 1u);
+    }
+}
+__global__ void k_zsort_scan(uint32_t n_layers, uint32_t* hist) {   // single thread: n_layers <= 4096
+    uint32_t acc = 0;
+    for (uint32_t i = 0; i < n_layers; ++i) {
+        const uint32_t c = hist[i];
+        hist[i] = acc;
+        acc += c;
+    }
+}
+__global__ void k_zsort_scatter(const TileJob* jobs, const uint32_t* n_jobs, uint32_t cap, uint32_t z0, uint32_t tile,
+                                uint32_t n_layers, uint32_t* hist, uint32_t* order) {
+    const uint32_t n = min(*n_jobs, cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t layer = min((jobs[i].z - z0) / tile, n_layers - 1u);
+        order[atomicAdd(&hist[n_layers - 1u - layer], 1u)] = i;
+    }
+}
+void launch_leaf_zsort(const TileJob* jobs, const uint32_t* n_jobs, uint32_t cap, uint32_t z0, uint32_t tile,
+                       uint32_t n_layers, uint32_t* hist, uint32_t* order, cudaStream_t s) {
+    cudaMemsetAsync(hist, 0, size_t(n_layers) * 4, s);
+    k_zsort_hist<<<296, 256, 0, s>>>(jobs, n_jobs, cap, z0, tile, n_layers, hist);
+    k_zsort_scan<<<1, 1, 0, s>>>(n_layers, hist);
+    k_zsort_scatter<<<296, 256, 0, s>>>(jobs, n_jobs, cap, z0, tile, n_layers, hist, order);
+}
 
 // Gradient interpreter (VmGradSliceEval, vm/mod.rs:1097-1396)
 template <class Input>

@@ -150,6 +150,7 @@ struct FillParams {
 
 struct VoxelParams {
     uint32_t tile, width, height;
+    const uint32_t* order;      // leaf jobs sorted front to back (descending z), or null
     Mat4 mat;
     const TileJob* jobs;
     uint32_t cap_jobs;
@@ -199,6 +200,9 @@ void launch_octree_leaf(const OctreeLeafParams& p, int blocks, cudaStream_t s);
 void launch_octree_grads(const OctreeLeafParams& p, int blocks, cudaStream_t s);
 void launch_interval_level_3d(const LevelParams& p, int blocks, cudaStream_t s);
 void launch_voxels_3d(const VoxelParams& p, int blocks, cudaStream_t s);
+// Counting sort of the leaf jobs by descending Z layer: hist/offsets are device scratch of n_layers+1 words
+void launch_leaf_zsort(const TileJob* jobs, const uint32_t* n_jobs, uint32_t cap, uint32_t z0, uint32_t tile,
+                       uint32_t n_layers, uint32_t* hist, uint32_t* order, cudaStream_t s);
 void launch_normals_3d(const NormalParams& p, cudaStream_t s);
 void launch_merge_slabs(const void* const* d_slabs, uint32_t n_slabs, uint32_t n_pixels, uint32_t depth, void* out,
                         cudaStream_t s);

@@ -31,3 +31,39 @@ def z_slab(rank: int, world: int, depth: int, root_tile: int = 128):
         raise ValueError(f"{n_layers} root-tile layers do not split evenly over {world} ranks")
     per = n_layers // world
     return rank * per * root_tile, (rank + 1) * per * root_tile
+
+
+def render2d_bands(shape, cfg, image, gathered, group=None):
+    """One sharded 2D frame: this rank renders its band of root-tile rows into `image`
+    (a CUDA tensor [H, W] float32), then ONE all-gather assembles all bands into `gathered`.
+    Enqueues on the current stream; returns `gathered`."""
+    import torch.distributed as dist
+    from dataclasses import replace
+    from .shape import render2d
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    t0 = (cfg.tile_sizes[0] if cfg.tile_sizes else 128)
+    rows = band_rows(rank, world, cfg.height, t0)
+    render2d(shape, replace(cfg, root_rows=rows), out=image, asynchronous=True)
+    y0, y1 = band_pixels(rows, cfg.width, cfg.height, t0)
+    dist.all_gather_into_tensor(gathered, image[y0:y1], group=group)
+    return gathered
+
+
+def render3d_zslabs(shape, cfg, slab, gathered, out, group=None):
+    """One sharded 3D render (north star: Z slabs + a single all-gather): this rank renders its
+    slab into `slab` ([H, W, 4] float32 CUDA tensor viewed as GeometryPixel, no final clamp), all
+    slabs are gathered into `gathered` ([world, H, W, 4]) and merged per pixel into `out`."""
+    import ctypes as C
+    import torch.distributed as dist
+    from dataclasses import replace
+    from . import _lib
+    from .shape import render3d, _ck
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    t0 = (cfg.tile_sizes[0] if cfg.tile_sizes else 128)
+    zr = z_slab(rank, world, cfg.depth, t0)
+    render3d(shape, replace(cfg, z_range=zr, clamp=False), out=slab, asynchronous=True)
+    dist.all_gather_into_tensor(gathered, slab, group=group)
+    ptrs = (C.c_void_p * world)(*[gathered[r].data_ptr() for r in range(world)])
+    _ck(_lib.load().fc_merge_slabs(shape.cuda._h, ptrs, world, cfg.width, cfg.height, cfg.depth,
+                                   C.c_void_p(out.data_ptr())))
+    return out

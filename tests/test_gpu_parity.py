@@ -388,3 +388,27 @@ def test_octree_gyroid_sphere(orc, cuda):
     cell = 2.0 / 2 ** 6
     assert np.all(np.abs(gc["pos"][present] - oc["pos"][present]) <= cell / 1000)   # the 16^4-ary search may land one bracket apart
     assert np.isclose(gc["grad"][present], oc["grad"][present], rtol=1e-2, atol=1e-2).mean() > 0.999
+
+
+def test_render_into_pinned_host_memory(cuda, monkeypatch):
+    """Host output buffers: staged + DMA copy by default, written directly by the kernels when
+    FIDGET_B200_ZEROCOPY=1 (page-locked memory); both give the same image."""
+    import torch
+    for zc in ("0", "1"):
+        monkeypatch.setenv("FIDGET_B200_ZEROCOPY", zc)
+        _check_pinned(cuda)
+
+
+def _check_pinned(cuda):
+    import torch
+    gs = fb.CudaShape.from_vm(cuda, model_text("prospero.vm"))
+    ref = fb.render2d(gs, fb.RenderConfig2D(1024, 1024))
+    pinned = torch.empty((1024, 1024), dtype=torch.float32).pin_memory()
+    pinned.fill_(123.0)
+    fb.render2d(gs, fb.RenderConfig2D(1024, 1024), out=pinned.numpy())
+    assert np.array_equal(pinned.numpy().view(np.uint32), ref.view(np.uint32))
+    col = fb.CudaShape.from_vm(cuda, model_text("colonnade.vm"))
+    ref3 = fb.render3d(col, fb.RenderConfig3D(256, 256, 256))
+    p3 = torch.zeros((256, 256, 4), dtype=torch.float32).pin_memory()
+    fb.render3d(col, fb.RenderConfig3D(256, 256, 256), out=p3.numpy())
+    assert np.array_equal(p3.numpy().view(np.uint32).reshape(256, 256, 4), ref3.view(np.uint32).reshape(256, 256, 4))
