@@ -116,9 +116,6 @@ struct Render3DConfig {
     int threads = 1;
     std::vector<float> var_values;
     uint32_t first_root = 0, n_roots = 0;
-    // Z range restriction [z_begin, z_end) in voxels for slab sharding tests;
-    // z_end = 0 means full depth.  Root tiles outside the slab are skipped.
-    uint32_t z_begin = 0, z_end = 0;
 };
 void render3d(const TapeP& tape, const Render3DConfig& cfg, GeometryPixel* out, TileStats* stats);
 
