@@ -820,7 +820,7 @@ int32_t fc_render2d(fc_ctx* c, const fc_tape* tape, const fc_render2d_cfg* cfg, 
         p.fills = c->fills[l].as<FillRec>();
         p.cap_fills = uint32_t(level_tiles[l + 1]);
         p.arena = c->arena.as<uint2>();
-        p.arena_cap = c->arena.cap / sizeof(uint2);
+        p.arena_cap = std::min<uint64_t>(c->arena.cap, c->arena_bytes) / sizeof(uint2);
         p.choice_scratch = c->choice_scratch.as<uint32_t>();
         p.choice_words = choice_words;
         p.ctr = c->counters.as<Counters>();
@@ -1006,7 +1006,7 @@ int32_t fc_render3d(fc_ctx* c, const fc_tape* tape, const fc_render3d_cfg* cfg, 
         p.jobs_out = c->jobs[l + 1].as<TileJob>();
         p.cap_out = uint32_t(level_cap[l + 1]);
         p.arena = c->arena.as<uint2>();
-        p.arena_cap = c->arena.cap / sizeof(uint2);
+        p.arena_cap = std::min<uint64_t>(c->arena.cap, c->arena_bytes) / sizeof(uint2);
         p.choice_scratch = c->choice_scratch.as<uint32_t>();
         p.choice_words = choice_words;
         p.ctr = c->counters.as<Counters>();
@@ -1188,7 +1188,7 @@ int32_t fc_octree_sample(fc_ctx* c, const fc_tape* tape, const fc_octree_cfg* cf
         p.jobs_out = c->jobs[l + 1].as<TileJob>();
         p.cap_out = uint32_t(level_cap[l + 1]);
         p.arena = c->arena.as<uint2>();
-        p.arena_cap = c->arena.cap / sizeof(uint2);
+        p.arena_cap = std::min<uint64_t>(c->arena.cap, c->arena_bytes) / sizeof(uint2);
         p.choice_scratch = c->choice_scratch.as<uint32_t>();
         p.choice_words = choice_words;
         p.ctr = c->counters.as<Counters>();

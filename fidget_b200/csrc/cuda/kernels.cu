@@ -479,13 +479,74 @@ void launch_interval_level_3d(const LevelParams& p, int blocks, cudaStream_t s) 
     k_interval_level<3><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(p);
 }
 
+// Four-points-per-lane f32 interpreter (leaf voxels): decode, dispatch and register-file traffic
+// are amortised over four points.
+__device__ __forceinline__ float4 f32x4_unary(uint32_t op, float4 a) {
+    switch (op) {
+        case OP_NEG: return make_float4(-a.x, -a.y, -a.z, -a.w);
+        case OP_ABS: return make_float4(fabsf(a.x), fabsf(a.y), fabsf(a.z), fabsf(a.w));
+        case OP_SQRT: return make_float4(sqrtf(a.x), sqrtf(a.y), sqrtf(a.z), sqrtf(a.w));
+        case OP_SQUARE: return make_float4(a.x * a.x, a.y * a.y, a.z * a.z, a.w * a.w);
+        default: return make_float4(f32_unary(op, a.x), f32_unary(op, a.y), f32_unary(op, a.z), f32_unary(op, a.w));
+    }
+}
+__device__ __forceinline__ float4 f32x4_binary(uint32_t op, float4 a, float4 b) {
+    switch (op) {
+        case OP_ADD: return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+        case OP_SUB: return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+        case OP_MUL: return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+        case OP_MIN: return make_float4(f_min(a.x, b.x), f_min(a.y, b.y), f_min(a.z, b.z), f_min(a.w, b.w));
+        case OP_MAX: return make_float4(f_max(a.x, b.x), f_max(a.y, b.y), f_max(a.z, b.z), f_max(a.w, b.w));
+        default: return make_float4(f32_binary(op, a.x, b.x), f32_binary(op, a.y, b.y), f32_binary(op, a.z, b.z),
+                                    f32_binary(op, a.w, b.w));
+    }
+}
+template <class Input>
+__device__ __forceinline__ float4 run_f32x4(const uint2* __restrict__ tape, uint32_t n_ops, float4* slots, Input input) {
+    float4 result = make_float4(nanf_(), nanf_(), nanf_(), nanf_());
+    if (n_ops == 0) return result;
+    uint2 w = __ldg(tape);
+    for (uint32_t i = 0; i < n_ops; ++i) {
+        const uint2 nxt = __ldg(tape + (i + 1 < n_ops ? i + 1 : i));
+        Dec d(w.x);
+        const float imm = __uint_as_float(w.y);
+        const float4 sl = slots[d.lhs], sr = slots[d.rhs];
+        const float4 im = make_float4(imm, imm, imm, imm);
+        const float4 a = d.form == F_IR ? im : sl;
+        const float4 b = d.form == F_RI ? im : sr;
+        float4 r;
+        if (d.op >= OP_ADD) {
+            if (d.op == OP_MEM) {
+                if (d.form == F_RI) slots[d.out] = slots[MEM_BASE + w.y];
+                else slots[MEM_BASE + w.y] = sl;
+                w = nxt;
+                continue;
+            }
+            r = f32x4_binary(d.op, a, b);
+        } else if (d.op >= OP_NEG) {
+            r = f32x4_unary(d.op, sl);
+        } else if (d.op == OP_COPY) {
+            r = d.form == F_RI ? im : sl;
+        } else if (d.op == OP_INPUT) {
+            r = input(w.y);
+        } else {
+            if (w.y == 0) result = sl;
+            w = nxt;
+            continue;
+        }
+        slots[d.out] = r;
+        w = nxt;
+    }
+    return result;
+}
+
 // ---------------------------------------------------------------------------
 // K2 (3D): leaf voxels.  One warp per leaf tile; each lane owns two XY columns
 // and walks Z front to back (k descending), two points per tape pass; the
 // warp stops as soon as every column has hit the surface (voxel.rs:359-447).
 __global__ void __launch_bounds__(128) k_voxels_3d(const __grid_constant__ VoxelParams p) {
     const int lane = threadIdx.x & 31;
-    float2 slots[REG_SLOTS];
+    float4 slots[REG_SLOTS];
     const uint32_t n_jobs = min(p.ctr->n_jobs[p.list], p.cap_jobs);
     const uint32_t T = p.tile, ncol = T * T;
     unsigned long long shaded = 0;
@@ -511,23 +572,31 @@ __global__ void __launch_bounds__(128) k_voxels_3d(const __grid_constant__ Voxel
             const uint32_t zmax = cz + T;
             bool done0 = !in0 || uint32_t(p.heightmap[size_t(gy0) * p.width + gx0] >> 32) >= zmax;
             bool done1 = !in1 || uint32_t(p.heightmap[size_t(gy1) * p.width + gx1] >> 32) >= zmax;
-            for (int k = int(T) - 1; k >= 0; --k) {
+            // two Z levels per tape pass: (column 0, column 1) x (k, k - 1)
+            for (int k = int(T) - 1; k >= 0; k -= 2) {
                 if (__all_sync(FULL, done0 && done1)) break;
-                float x0, y0, z0, x1, y1, z1;
-                xform_f32(p.mat, float(gx0), float(gy0), float(cz + uint32_t(k)), x0, y0, z0);
-                xform_f32(p.mat, float(gx1), float(gy1), float(cz + uint32_t(k)), x1, y1, z1);
-                const float2 X = make_float2(x0, x1), Y = make_float2(y0, y1), Z = make_float2(z0, z1);
-                const float2 r = run_f32x2(tape, tr.n_ops, slots, [&](uint32_t i) {
-                    return pick_input(p.vb, i, X, Y, Z, [](float f) { return make_float2(f, f); });
+                const int k2 = k > 0 ? k - 1 : 0;
+                float xa, ya, za, xb, yb, zb, xc, yc, zc, xd, yd, zd;
+                xform_f32(p.mat, float(gx0), float(gy0), float(cz + uint32_t(k)), xa, ya, za);
+                xform_f32(p.mat, float(gx1), float(gy1), float(cz + uint32_t(k)), xb, yb, zb);
+                xform_f32(p.mat, float(gx0), float(gy0), float(cz + uint32_t(k2)), xc, yc, zc);
+                xform_f32(p.mat, float(gx1), float(gy1), float(cz + uint32_t(k2)), xd, yd, zd);
+                const float4 X = make_float4(xa, xb, xc, xd), Y = make_float4(ya, yb, yc, yd), Z = make_float4(za, zb, zc, zd);
+                const float4 r = run_f32x4(tape, tr.n_ops, slots, [&](uint32_t i) {
+                    return pick_input(p.vb, i, X, Y, Z, [](float f) { return make_float4(f, f, f, f); });
                 });
-                const unsigned long long key = ((unsigned long long)(cz + uint32_t(k) + 1u) << 32) | id;
+                const unsigned long long key_hi = ((unsigned long long)(cz + uint32_t(k) + 1u) << 32) | id;
+                const unsigned long long key_lo = ((unsigned long long)(cz + uint32_t(k2) + 1u) << 32) | id;
+                const bool two = k > 0;
                 if (!done0) {
-                    ++shaded;
-                    if (r.x < 0.0f) { atomicMax(&p.heightmap[size_t(gy0) * p.width + gx0], key); done0 = true; }
+                    shaded += two ? 2 : 1;
+                    if (r.x < 0.0f) { atomicMax(&p.heightmap[size_t(gy0) * p.width + gx0], key_hi); done0 = true; }
+                    else if (two && r.z < 0.0f) { atomicMax(&p.heightmap[size_t(gy0) * p.width + gx0], key_lo); done0 = true; }
                 }
                 if (!done1) {
-                    ++shaded;
-                    if (r.y < 0.0f) { atomicMax(&p.heightmap[size_t(gy1) * p.width + gx1], key); done1 = true; }
+                    shaded += two ? 2 : 1;
+                    if (r.y < 0.0f) { atomicMax(&p.heightmap[size_t(gy1) * p.width + gx1], key_hi); done1 = true; }
+                    else if (two && r.w < 0.0f) { atomicMax(&p.heightmap[size_t(gy1) * p.width + gx1], key_lo); done1 = true; }
                 }
             }
         }

@@ -412,3 +412,84 @@ def _check_pinned(cuda):
     p3 = torch.zeros((256, 256, 4), dtype=torch.float32).pin_memory()
     fb.render3d(col, fb.RenderConfig3D(256, 256, 256), out=p3.numpy())
     assert np.array_equal(p3.numpy().view(np.uint32).reshape(256, 256, 4), ref3.view(np.uint32).reshape(256, 256, 4))
+
+
+# ---------------------------------------------------------------------------
+# Edge cases and error behaviour of the C ABI
+@pytest.mark.parametrize("w,h", [(1, 1), (7, 5), (100, 37), (129, 257), (640, 480)])
+def test_render2d_ragged_sizes(orc, cuda, w, h):
+    ot, gs = _pair(orc, cuda, "hi.vm")
+    o_img, o_st = orc.render2d(ot, w, h)
+    g_img, g_st = fb.render2d(gs, fb.RenderConfig2D(w, h), stats=True)
+    assert np.array_equal(g_img.view(np.uint32), o_img.view(np.uint32))
+    assert g_st["evaluated"] == o_st["evaluated"] and g_st["pixels"] == o_st["pixels"]
+
+
+@pytest.mark.parametrize("ts", [(128, 16), (64, 8), (256, 32, 8), (8,)])
+def test_render2d_custom_tile_sizes(orc, cuda, ts):
+    # EvalConfig::tile_sizes (pixel.rs:42-57); (128, 16) is the JIT's default (fidget-jit/src/lib.rs:984)
+    ot, gs = _pair(orc, cuda, "prospero.vm")
+    o_img, o_st = orc.render2d(ot, 512, 512, tile_sizes=ts, threads=8)
+    g_img, g_st = fb.render2d(gs, fb.RenderConfig2D(512, 512, tile_sizes=ts), stats=True)
+    assert np.array_equal(g_img.view(np.uint32), o_img.view(np.uint32))
+    assert g_st["evaluated"] == o_st["evaluated"]
+
+
+def test_render2d_pixel_perfect_and_z(orc, cuda):
+    ot, gs = _pair(orc, cuda, "colonnade.vm")
+    for z in (0.0, 0.3):
+        o_img, _ = orc.render2d(ot, 256, 256, z=z, pixel_perfect=True, threads=8)
+        g_img = fb.render2d(gs, fb.RenderConfig2D(256, 256, z=z, pixel_perfect=True))
+        assert np.array_equal(g_img.view(np.uint32), o_img.view(np.uint32))
+
+
+def test_render3d_ragged_volume(orc, cuda):
+    ot = orc.Tape.from_data(_sphere_tape(orc.Context, 0.7))
+    gs = fb.CudaShape(cuda, _sphere_tape(fb.Context, 0.7))
+    o_img, _ = orc.render3d(ot, 100, 60, 90, threads=8)
+    g_img = fb.render3d(gs, fb.RenderConfig3D(100, 60, 90))
+    _cmp3d(g_img, o_img, exact_normals=True)
+
+
+def test_bad_inputs_fail_loudly(cuda):
+    import ctypes as C
+    from fidget_b200 import _lib
+    lib = _lib.load()
+    h = C.c_void_p()
+    words = (C.c_uint32 * 4)(0xFFFFFFFF, 0, 0xFFFFFFFF, 0xFFFFFFFE)          # broken end marker
+    assert lib.fc_tape_create(cuda._h, words, 4, 1, 0, 1, 1, 0, C.byref(h)) == -1
+    assert b"marker" in lib.fc_last_error()
+    words = (C.c_uint32 * 6)(0xFFFFFFFF, 0, 0x00FFFF63, 0, 0xFFFFFFFF, 0xFFFFFFFF)   # opcode 0x63
+    assert lib.fc_tape_create(cuda._h, words, 6, 1, 0, 1, 1, 0, C.byref(h)) == -1
+    gs = fb.CudaShape.from_vm(cuda, model_text("hi.vm"))
+    with pytest.raises(fb.CudaError):
+        gs.simplify(np.zeros(3, dtype=np.uint8))                               # BadChoiceSlice
+    with pytest.raises(fb.CudaError):
+        gs.simplify(np.zeros(gs.choice_count, dtype=np.uint8))                 # Choice::Unknown in a trace
+    with pytest.raises(fb.CudaError):
+        fb.render2d(gs, fb.RenderConfig2D(64, 64, tile_sizes=(8, 32)))         # TileSizeError::BadTileOrder
+    with pytest.raises(fb.CudaError):
+        fb.render2d(gs, fb.RenderConfig2D(0, 64))
+    cuda.set_arena_bytes(1 << 20)                                              # arena far too small for prospero
+    try:
+        big = fb.CudaShape.from_vm(cuda, model_text("prospero.vm"))
+        with pytest.raises(fb.CudaError) as e:
+            fb.render2d(big, fb.RenderConfig2D(2048, 2048))
+        assert e.value.code == -4                                              # FC_ERR_ARENA, not a silent fallback
+    finally:
+        cuda.set_arena_bytes(1 << 30)
+    img = fb.render2d(fb.CudaShape.from_vm(cuda, model_text("prospero.vm")), fb.RenderConfig2D(512, 512))
+    assert fb.pixel_inside(img).any()
+
+
+def test_constant_and_single_axis_shapes(orc, cuda):
+    for build in (lambda c: c.constant(1.5), lambda c: c.x(), lambda c: c.sub(c.y(), c.constant(0.25)),
+                  lambda c: c.neg(c.z())):
+        o_ctx, g_ctx = orc.Context(), fb.Context()
+        ot = orc.Tape.from_data(o_ctx.tape(build(o_ctx)))
+        gs = fb.CudaShape(cuda, g_ctx.tape(build(g_ctx)))
+        o_img, _ = orc.render2d(ot, 96, 96)
+        assert np.array_equal(fb.render2d(gs, fb.RenderConfig2D(96, 96)).view(np.uint32), o_img.view(np.uint32))
+        o3, _ = orc.render3d(ot, 64, 64, 64)
+        g3 = fb.render3d(gs, fb.RenderConfig3D(64, 64, 64))
+        _cmp3d(g3, o3, exact_normals=True)
