@@ -33,11 +33,24 @@ if "bear" in which:
     out = torch.empty((n, n, 4), dtype=torch.float32, device="cuda")
     st = time_render3d(shape, fb.RenderConfig3D(n, n, n, timing=True), out)
     ms = st["stage_ms"]
+    from oracle import oracle as orc
+    ot = orc.Tape.from_vm(model("bear.vm"))
+    threads = os.cpu_count()
+    t0 = time.perf_counter()
+    orc.render3d(ot, n, n, n, threads=threads)
+    cpu_s = time.perf_counter() - t0
     print(json.dumps({"config": "bear.vm 3D heightmap+normals 1024^3", "ms": ms[15], "Mvoxels_per_s": n ** 3 / ms[15] / 1e3,
+                      "cpu_oracle_ms": cpu_s * 1e3, "cpu_threads": threads,
                       "levels_ms": ms[:5], "voxels_ms": ms[9], "normals_ms": ms[10], "voxel_evals": st["pixels"],
                       "grad_evals": st["grads"], "arena_MB": st["arena_bytes_used"] / 1e6}))
 if "gyroid" in which:
     shape = fb.CudaShape.from_vm(cuda, model("gyroid-sphere.vm"))
+    from oracle import oracle as orc
+    ot = orc.Tape.from_vm(model("gyroid-sphere.vm"))
+    t0 = time.perf_counter()
+    orc.octree_sample(ot, 7)
+    print(json.dumps({"config": "gyroid-sphere octree sampler depth 7, CPU oracle (1 thread)",
+                      "ms": (time.perf_counter() - t0) * 1e3}))
     for depth in (7, 8, 9):
         fb.octree_sample(shape, depth, capacity=8 << 20 if depth == 9 else None)   # warm-up
         t0 = time.perf_counter()

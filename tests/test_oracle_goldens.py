@@ -286,3 +286,73 @@ def test_float_slice_binary_canonical(orc, op):
             want = (_canon(op, kk, args) if imm_first else _canon(op, args, kk)).astype(np.float32)
             assert np.array_equal(np.isnan(got), np.isnan(want)) and \
                 np.array_equal(got[~np.isnan(got)], want[~np.isnan(want)]), (op, k, imm_first)
+
+
+# ---------------------------------------------------------------------------
+# Octree sampler: the reference's mesh tests that only depend on the sampled edge crossings
+def _mesh_sphere(ctx, center, radius):
+    # fidget-mesh/src/octree.rs:1075-1082
+    x, y, z = ctx.x(), ctx.y(), ctx.z()
+    sx = ctx.square(ctx.sub(x, ctx.constant(center[0])))
+    sy = ctx.square(ctx.sub(y, ctx.constant(center[1])))
+    sz = ctx.square(ctx.sub(z, ctx.constant(center[2])))
+    return ctx.sub(ctx.sqrt(ctx.add(ctx.add(sx, sy), sz)), ctx.constant(radius))
+
+
+def _mesh_cube(ctx, bx, by, bz):
+    # octree.rs:1084-1090
+    x, y, z = ctx.x(), ctx.y(), ctx.z()
+    xb = ctx.max(ctx.sub(ctx.constant(bx[0]), x), ctx.sub(x, ctx.constant(bx[1])))
+    yb = ctx.max(ctx.sub(ctx.constant(by[0]), y), ctx.sub(y, ctx.constant(by[1])))
+    zb = ctx.max(ctx.sub(ctx.constant(bz[0]), z), ctx.sub(z, ctx.constant(bz[1])))
+    return ctx.max(ctx.max(xb, yb), zb)
+
+
+def _edge_points(leaves):
+    present = ((leaves["present"][:, None] >> np.arange(12)[None, :]) & 1).astype(bool)
+    return leaves["pos"][present]
+
+
+def test_octree_sphere_edge_vertices(orc):
+    # octree.rs:1181-1214 (test_sphere_verts): depth 1, radius 0.2: the 6 edge vertices sit on the axes
+    ctx = orc.Context()
+    t = orc.Tape.from_data(ctx.tape(_mesh_sphere(ctx, (0, 0, 0), 0.2)))
+    leaves, st = orc.octree_sample(t, 1)
+    assert st["leaf_surface"] == 8
+    pts = _edge_points(leaves)
+    assert np.all((pts != 0).sum(axis=1) == 1)
+    assert np.all(np.abs(np.linalg.norm(pts, axis=1) - 0.2) < 2.0 / 65535)
+    assert len(np.unique(np.round(pts, 5), axis=0)) == 6
+
+
+def test_octree_cube_edge_positions(orc):
+    # octree.rs:1235-1276 (test_cube_verts)
+    ctx = orc.Context()
+    bx, by, bz = (-0.1, 0.6), (-0.2, 0.75), (-0.3, 0.4)
+    t = orc.Tape.from_data(ctx.tape(_mesh_cube(ctx, bx, by, bz)))
+    leaves, _ = orc.octree_sample(t, 1)
+    pts = _edge_points(leaves)
+    assert len(pts) > 0
+    eps = 2.0 / 65535
+    for v in pts:
+        nz = v != 0
+        assert nz.sum() == 1
+        a = int(np.argmax(nz))
+        lo, hi = (bx, by, bz)[a]
+        assert abs(v[a] - lo) < eps or abs(v[a] - hi) < eps, v
+
+
+def test_octree_cube_single_edge(orc):
+    # octree.rs:1093-1107 (test_cube_edge): depth 0, 4 crossings (+ 1 QEF vertex = the 5 verts of the reference)
+    ctx = orc.Context()
+    f = 2.0
+    t = orc.Tape.from_data(ctx.tape(_mesh_cube(ctx, (-f, f), (-f, 0.3), (-f, 0.6))))
+    leaves, _ = orc.octree_sample(t, 0)
+    assert len(leaves) == 1 and leaves[0]["n_edges"] == 4
+    pts = _edge_points(leaves)
+    for v in pts:
+        assert abs(v[1] - 0.3) < 1e-3 or abs(v[2] - 0.6) < 1e-3
+    # gradients at the crossings are the face normals
+    present = ((leaves["present"][:, None] >> np.arange(12)[None, :]) & 1).astype(bool)
+    g = leaves["grad"][present][:, :3]
+    assert np.all((np.abs(g) == 1).sum(axis=1) == 1)
