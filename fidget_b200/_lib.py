@@ -115,6 +115,15 @@ CUDA_API = {
     "fc_render3d": (_i32, [_vp, _vp, _P(FcRender3dCfg), _vp, _P(FcRenderStats)]),
     "fc_merge_slabs": (_i32, [_vp, _P(_vp), _u32, _u32, _u32, _u32, _vp]),
     "fc_octree_sample": (_i32, [_vp, _vp, _P(FcOctreeCfg), _vp, _u64, _P(_u64), _P(FcOctreeStats)]),
+    "fc_denoise_normals": (_i32, [_vp, _vp, _u32, _u32, _vp]),
+    "fc_compute_ssao": (_i32, [_vp, _vp, _u32, _u32, _u32, _vp, _u32, _vp, _u32, _vp]),
+    "fc_blur_ssao": (_i32, [_vp, _vp, _u32, _u32, _vp]),
+    "fc_apply_shading": (_i32, [_vp, _vp, _u32, _u32, _u32, _i32, _vp, _u32, _vp, _u32, _vp]),
+    "fc_shade_with_occlusion": (_i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp]),
+    "fc_normals_to_color": (_i32, [_vp, _vp, _u32, _u32, _vp]),
+    "fc_to_rgba_bitmap": (_i32, [_vp, _vp, _u32, _u32, _i32, _vp]),
+    "fc_to_debug_bitmap": (_i32, [_vp, _vp, _u32, _u32, _vp]),
+    "fc_to_rgba_distance": (_i32, [_vp, _vp, _u32, _u32, _vp]),
 }
 
 

@@ -233,6 +233,46 @@ typedef struct fc_octree_stats {
 int32_t fc_octree_sample(fc_ctx* ctx, const fc_tape* tape, const fc_octree_cfg* cfg, fc_octree_leaf* out,
                          uint64_t cap, uint64_t* n_leaves, fc_octree_stats* stats /* may be NULL */);
 
+/* ---- post-processing effects (fidget-raster/src/effects.rs) ---------------- */
+/* Every image pointer may be a host or a device pointer (host images are staged
+ * through HBM); images are row-major width*height.  All results are bit-identical
+ * to the reference's arithmetic except fc_to_rgba_distance (exp/cos: within one
+ * 8-bit step). */
+
+/* effects::denoise_normals (effects.rs:17-36): back-facing normals are replaced by
+ * the best-scoring mean of four 3x3 neighbourhoods.  Not in place. */
+int32_t fc_denoise_normals(fc_ctx* ctx, const fc_geometry_pixel* image, uint32_t width, uint32_t height,
+                           fc_geometry_pixel* out);
+/* effects::compute_ssao (effects.rs:72-95).  `kernel`: n_kernel hemisphere samples
+ * (x,y,z each), `noise`: n_noise unit XY rotations (x,y each) -- the reference draws
+ * them from rand::rng() on every call (ssao_kernel(64) / ssao_noise(256),
+ * effects.rs:385-440), so they are inputs here.  out: width*height f32, NaN where
+ * the pixel is empty. */
+int32_t fc_compute_ssao(fc_ctx* ctx, const fc_geometry_pixel* image, uint32_t width, uint32_t height,
+                        uint32_t depth, const float* kernel, uint32_t n_kernel, const float* noise,
+                        uint32_t n_noise, float* out);
+/* effects::blur_ssao (effects.rs:98-115).  Not in place. */
+int32_t fc_blur_ssao(fc_ctx* ctx, const float* ssao, uint32_t width, uint32_t height, float* out);
+/* effects::apply_shading (effects.rs:42-66): three-light diffuse shading, optionally
+ * modulated by compute_ssao + blur_ssao (ssao != 0; then the tables are required).
+ * out_rgb: width*height*3 bytes (ColorImage). */
+int32_t fc_apply_shading(fc_ctx* ctx, const fc_geometry_pixel* image, uint32_t width, uint32_t height,
+                         uint32_t depth, int32_t ssao, const float* kernel, uint32_t n_kernel,
+                         const float* noise, uint32_t n_noise, uint8_t* out_rgb);
+/* The last stage of apply_shading alone (shade_pixel, effects.rs:118-154) with an
+ * already blurred occlusion map (or NULL). */
+int32_t fc_shade_with_occlusion(fc_ctx* ctx, const fc_geometry_pixel* image, uint32_t width, uint32_t height,
+                                uint32_t depth, const float* blurred_ssao, uint8_t* out_rgb);
+/* GeometryPixel::to_color per pixel (voxel.rs:136-153). out_rgb: width*height*3 bytes. */
+int32_t fc_normals_to_color(fc_ctx* ctx, const fc_geometry_pixel* image, uint32_t width, uint32_t height,
+                            uint8_t* out_rgb);
+/* effects::to_rgba_bitmap / to_debug_bitmap / to_rgba_distance (effects.rs:446-547) on a
+ * RawDistancePixel image (fc_render2d's output).  out_rgba: width*height*4 bytes. */
+int32_t fc_to_rgba_bitmap(fc_ctx* ctx, const float* image, uint32_t width, uint32_t height, int32_t transparent,
+                          uint8_t* out_rgba);
+int32_t fc_to_debug_bitmap(fc_ctx* ctx, const float* image, uint32_t width, uint32_t height, uint8_t* out_rgba);
+int32_t fc_to_rgba_distance(fc_ctx* ctx, const float* image, uint32_t width, uint32_t height, uint8_t* out_rgba);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,7 @@
 
 #include "../fidget_b200/csrc/host/host_capi.h"
 #include "octree.h"
+#include "effects.h"
 #include "vm.h"
 
 using namespace oracle;
@@ -175,5 +176,26 @@ int32_t orc_octree_sample(const orc_tape* t, uint32_t depth, const float* world_
     });
 }
 static_assert(sizeof(OctreeLeaf) == 348, "OctreeLeaf layout");
+
+// fidget-raster effects (oracle/effects.h); all images are host arrays, row-major
+void orc_denoise_normals(const void* image, uint32_t w, uint32_t h, void* out) {
+    denoise_normals(static_cast<const GeoPixel*>(image), w, h, static_cast<GeoPixel*>(out));
+}
+void orc_compute_ssao(const void* image, uint32_t w, uint32_t h, uint32_t d, const float* kernel, uint32_t nk,
+                      const float* noise, uint32_t nn, float* out) {
+    compute_ssao(static_cast<const GeoPixel*>(image), w, h, d, kernel, nk, noise, nn, out);
+}
+void orc_blur_ssao(const float* ssao, uint32_t w, uint32_t h, float* out) { blur_ssao(ssao, w, h, out); }
+void orc_apply_shading(const void* image, uint32_t w, uint32_t h, uint32_t d, const float* ssao, uint8_t* out) {
+    apply_shading(static_cast<const GeoPixel*>(image), w, h, d, ssao, out);
+}
+void orc_normals_to_color(const void* image, uint64_t n, uint8_t* out) {
+    normals_to_color(static_cast<const GeoPixel*>(image), n, out);
+}
+void orc_to_rgba_bitmap(const float* image, uint64_t n, int32_t transparent, uint8_t* out) {
+    to_rgba_bitmap(image, n, transparent != 0, out);
+}
+void orc_to_debug_bitmap(const float* image, uint64_t n, uint8_t* out) { to_debug_bitmap(image, n, out); }
+void orc_to_rgba_distance(const float* image, uint64_t n, uint8_t* out) { to_rgba_distance(image, n, out); }
 
 }  // extern "C"

@@ -276,3 +276,78 @@ def octree_sample(tape: Tape, depth: int, world_to_model=None):
              "leaf_empty": s[64], "leaf_full": s[65], "leaf_surface": s[66], "float_points": s[67],
              "grad_points": s[68]}
     return leaves, stats
+
+
+# ---- fidget-raster effects (oracle/effects.h) --------------------------------
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _u8p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def _geo(image):
+    image = np.ascontiguousarray(image, dtype=GEOMETRY_PIXEL)
+    assert image.ndim == 2
+    return image
+
+
+def denoise_normals(image):
+    image = _geo(image)
+    out = np.zeros_like(image)
+    lib().orc_denoise_normals(_vp(image), C.c_uint32(image.shape[1]), C.c_uint32(image.shape[0]), _vp(out))
+    return out
+
+
+def compute_ssao(image, depth, kernel, noise):
+    image = _geo(image)
+    k = np.ascontiguousarray(kernel, dtype=np.float32).reshape(-1, 3)
+    nz = np.ascontiguousarray(noise, dtype=np.float32).reshape(-1, 2)
+    out = np.zeros(image.shape, dtype=np.float32)
+    lib().orc_compute_ssao(_vp(image), C.c_uint32(image.shape[1]), C.c_uint32(image.shape[0]), C.c_uint32(depth),
+                           _fp(k), C.c_uint32(len(k)), _fp(nz), C.c_uint32(len(nz)), _fp(out))
+    return out
+
+
+def blur_ssao(ssao):
+    ssao = np.ascontiguousarray(ssao, dtype=np.float32)
+    out = np.zeros_like(ssao)
+    lib().orc_blur_ssao(_fp(ssao), C.c_uint32(ssao.shape[1]), C.c_uint32(ssao.shape[0]), _fp(out))
+    return out
+
+
+def apply_shading(image, depth, ssao=None):
+    """effects.rs:42-66 with the blurred occlusion map (or None) as an input."""
+    image = _geo(image)
+    out = np.zeros(image.shape + (3,), dtype=np.uint8)
+    s = None if ssao is None else _fp(np.ascontiguousarray(ssao, dtype=np.float32))
+    lib().orc_apply_shading(_vp(image), C.c_uint32(image.shape[1]), C.c_uint32(image.shape[0]), C.c_uint32(depth),
+                            s, _u8p(out))
+    return out
+
+
+def normals_to_color(image):
+    image = _geo(image)
+    out = np.zeros(image.shape + (3,), dtype=np.uint8)
+    lib().orc_normals_to_color(_vp(image), C.c_uint64(image.size), _u8p(out))
+    return out
+
+
+def _rgba(fn, image, *extra):
+    image = np.ascontiguousarray(image, dtype=np.float32)
+    out = np.zeros(image.shape + (4,), dtype=np.uint8)
+    fn(_fp(image), C.c_uint64(image.size), *extra, _u8p(out))
+    return out
+
+
+def to_rgba_bitmap(image, transparent=False):
+    return _rgba(lib().orc_to_rgba_bitmap, image, C.c_int32(int(transparent)))
+
+
+def to_debug_bitmap(image):
+    return _rgba(lib().orc_to_debug_bitmap, image)
+
+
+def to_rgba_distance(image):
+    return _rgba(lib().orc_to_rgba_distance, image)

@@ -11,7 +11,7 @@ import fidget_b200 as fb
 
 cuda = fb.CudaContext(0)
 cuda.set_arena_bytes(8 << 30)
-which = sys.argv[1:] or ["bear", "gyroid", "slab"]
+which = sys.argv[1:] or ["bear", "gyroid", "slab", "effects"]
 
 
 def model(name):
@@ -71,3 +71,52 @@ if "slab" in which:
                       "ms": ms[15], "Mvoxels_per_s_slab": n * n * 512 / ms[15] / 1e3, "levels_ms": ms[:5],
                       "voxels_ms": ms[9], "normals_ms": ms[10], "voxel_evals": st["pixels"],
                       "arena_MB": st["arena_bytes_used"] / 1e6}))
+if "effects" in which:
+    # fidget-raster's viewer post-processing on a device-resident bear.vm 1024^3 heightmap:
+    # HBM-bound byte work; GB/s = algorithmic bytes (read 16 B GeometryPixel + write result) / time
+    from fidget_b200 import effects as fx
+    from oracle import oracle as orc
+    shape = fb.CudaShape.from_vm(cuda, model("bear.vm"))
+    n = 1024
+    geo = torch.empty((n, n, 4), dtype=torch.float32, device="cuda")
+    fb.render3d(shape, fb.RenderConfig3D(n, n, n), out=geo)
+    den = torch.empty_like(geo)
+    ssao = torch.empty((n, n), dtype=torch.float32, device="cuda")
+    blur = torch.empty_like(ssao)
+    rgb = torch.empty((n, n, 3), dtype=torch.uint8, device="cuda")
+    rgba = torch.empty((4096, 4096, 4), dtype=torch.uint8, device="cuda")
+    img2d = torch.empty((4096, 4096), dtype=torch.float32, device="cuda")
+    fb.render2d(fb.CudaShape.from_vm(cuda, model("prospero.vm")), fb.RenderConfig2D(4096, 4096), out=img2d)
+    k, nz = fx.ssao_kernel(64), fx.ssao_noise(256)
+    cuda.set_stream(torch.cuda.current_stream().cuda_stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def timed(fn, reps=10):
+        fn()
+        best = 1e9
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b))
+        return best
+    px = n * n
+    cases = [
+        ("denoise_normals 1024^2", lambda: fx.denoise_normals(cuda, geo, out=den), px * 32),
+        ("compute_ssao 1024^2 (64 samples)", lambda: fx.compute_ssao(cuda, den, n, k, nz, out=ssao), px * 20),
+        ("blur_ssao 1024^2", lambda: fx.blur_ssao(cuda, ssao, out=blur), px * 8),
+        ("apply_shading(ssao) 1024^2 fused pipeline", lambda: fx.apply_shading(cuda, den, n, True, k, nz, out=rgb), px * 19),
+        ("apply_shading(no ssao) 1024^2", lambda: fx.apply_shading(cuda, den, n, False, out=rgb), px * 19),
+        ("to_rgba_bitmap 4096^2", lambda: fx.to_rgba_bitmap(cuda, img2d, out=rgba), 4096 * 4096 * 8),
+        ("to_rgba_distance 4096^2", lambda: fx.to_rgba_distance(cuda, img2d, out=rgba), 4096 * 4096 * 8),
+    ]
+    for name, fn, nbytes in cases:
+        ms = timed(fn)
+        print(json.dumps({"config": "effects: " + name, "ms": ms, "algorithmic_GB_per_s": nbytes / ms / 1e6}))
+    fx.apply_shading(cuda, den, n, True, k, nz, out=rgb)
+    den_h = den.cpu().numpy().view(fb.GEOMETRY_PIXEL).reshape(n, n)
+    t0 = time.perf_counter()
+    want = orc.apply_shading(den_h, n, orc.blur_ssao(orc.compute_ssao(den_h, n, k, nz)))
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    print(json.dumps({"config": "effects: apply_shading(ssao) 1024^2, CPU oracle (1 thread)", "ms": cpu_ms,
+                      "identical_to_gpu": bool(np.array_equal(want, rgb.cpu().numpy()))}))
