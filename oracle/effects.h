@@ -3,6 +3,10 @@
 // CPU restatement of fidget-raster's post-processing effects
 // (fidget-raster/src/effects.rs:13-547) and GeometryPixel::to_color
 // (fidget-raster/src/voxel.rs:136-153).
+//
+// PARITY UNPINNED BY REFERENCE VECTORS: effects.rs has no tests or fixtures and draws its SSAO
+// tables from rand::rng().  tests/test_effects_oracle.py checks this file against the source's
+// literal colour tables, closed-form cases and an independent float32 numpy transcription.
 #pragma once
 #include <cstdint>
 
