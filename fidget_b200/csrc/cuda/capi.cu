@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <atomic>
 #include <memory>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -115,12 +116,14 @@ struct Sched {
     uint64_t hash = 0;
     size_t n_clauses = 0;
     CoopRec* d_recs = nullptr;
+    CoopFwd* d_fwd = nullptr;
     uint32_t* d_wave_start = nullptr;
-    uint32_t n_waves = 0, tail_begin = 0, tail_end = 0;
+    uint32_t n_waves = 0, tail_begin = 0, tail_end = 0, n_slots = 0;
     std::vector<CoopSeg> segs;
     ~Sched() {
         cudaSetDevice(device);
         if (d_recs) cudaFree(d_recs);
+        if (d_fwd) cudaFree(d_fwd);
         if (d_wave_start) cudaFree(d_wave_start);
     }
 };
@@ -190,7 +193,7 @@ static bool build_schedule(const std::vector<uint2>& cl, std::vector<CoopRec>& r
     };
     uint32_t i = tail_begin, serial_start = tail_begin;
     auto flush_serial = [&](uint32_t upto) {
-        if (upto > serial_start) segs.push_back(CoopSeg{serial_start, upto, 0});
+        if (upto > serial_start) segs.push_back(CoopSeg{serial_start, upto, 0, COOP_NONE});
         serial_start = upto;
     };
     while (i < tend) {
@@ -206,7 +209,7 @@ static bool build_schedule(const std::vector<uint2>& cl, std::vector<CoopRec>& r
         }
         if (j - i >= 8 && segs.size() + 3 <= size_t(COOP_MAX_SEGS)) {
             flush_serial(i);
-            segs.push_back(CoopSeg{i, j, 1});
+            segs.push_back(CoopSeg{i, j, 1, COOP_NONE});
             serial_start = j;
             i = j;
         } else {
@@ -215,6 +218,83 @@ static bool build_schedule(const std::vector<uint2>& cl, std::vector<CoopRec>& r
     }
     flush_serial(tend);
     return segs.size() <= size_t(COOP_MAX_SEGS);
+}
+
+// Forward view of a schedule: colour the values with slots.  Execution steps are the waves,
+// then every clause of a serial tail run, then each chain run as a whole; a slot is free again
+// from the step after the last reader of its value.  A chain value read only by the next clause
+// of the same chain needs no slot (the scan never loads it); in a chain clause the operand that
+// is the previous chain value is marked COOP_NONE and the run's starting value goes to
+// segs[].start_slot.  Returns the number of slots, or 0 if they do not fit 16 bits.
+static uint32_t colour_slots(const std::vector<CoopRec>& recs, const std::vector<uint32_t>& wave_start,
+                             std::vector<CoopSeg>& segs, std::vector<CoopFwd>& fwd) {
+    const size_t m = recs.size();
+    std::vector<uint32_t> step(m, 0), idx_of_pos(m, 0), chain_of(m, 0);   // chain_of: 1 + segment index for chain clauses
+    uint32_t st = 0;
+    for (size_t w = 0; w + 1 < wave_start.size(); ++w, ++st)
+        for (uint32_t i = wave_start[w]; i < wave_start[w + 1]; ++i) step[i] = st;
+    for (size_t k = 0; k < segs.size(); ++k) {
+        if (segs[k].chain) {
+            for (uint32_t i = segs[k].begin; i < segs[k].end; ++i) { step[i] = st; chain_of[i] = uint32_t(k) + 1; }
+            ++st;
+        } else {
+            for (uint32_t i = segs[k].begin; i < segs[k].end; ++i) step[i] = st++;
+        }
+    }
+    for (size_t i = 0; i < m; ++i) idx_of_pos[recs[i].p] = uint32_t(i);
+    // last reading step of every value and whether anything but its chain successor reads it
+    std::vector<uint32_t> last_read(m, 0), n_other(m, 0);
+    std::vector<uint8_t> has_reader(m, 0);
+    for (size_t i = 0; i < m; ++i) {
+        for (uint16_t src : {recs[i].ia, recs[i].ib}) {
+            if (src == COOP_NONE) continue;
+            const uint32_t d = idx_of_pos[src];
+            last_read[d] = std::max(last_read[d], step[i]);
+            has_reader[d] = 1;
+            const bool chain_succ = chain_of[i] && chain_of[d] == chain_of[i] && d + 1 == i;
+            if (!chain_succ) ++n_other[d];
+        }
+    }
+    std::vector<uint16_t> slot(m, uint16_t(COOP_NONE));
+    std::vector<uint32_t> free_list;
+    std::vector<std::vector<uint32_t>> release(st + 2);   // release[s]: record indices whose slot is free from step s on
+    uint32_t n_slots = 0;
+    // records sorted by step: waves and tail are already in step order
+    uint32_t cur = 0;
+    for (size_t i = 0; i < m; ++i) {
+        while (cur <= step[i]) {
+            for (uint32_t d : release[cur]) free_list.push_back(slot[d]);
+            ++cur;
+        }
+        const bool is_output = ((recs[i].x & 0xff) >> 2) == OP_OUTPUT;
+        const bool chain_internal = chain_of[i] && has_reader[i] && n_other[i] == 0 && i + 1 < m && chain_of[i + 1] == chain_of[i];
+        if (is_output || chain_internal) continue;
+        uint32_t sl;
+        if (!free_list.empty()) { sl = free_list.back(); free_list.pop_back(); }
+        else sl = n_slots++;
+        if (sl >= COOP_NONE) return 0;
+        slot[i] = uint16_t(sl);
+        const uint32_t rel = (has_reader[i] ? last_read[i] : step[i]) + 1;
+        release[std::min<uint32_t>(rel, st + 1)].push_back(uint32_t(i));
+    }
+    fwd.resize(m);
+    for (size_t i = 0; i < m; ++i) {
+        CoopFwd f;
+        f.x = recs[i].x; f.y = recs[i].y; f.cidx = recs[i].cidx;
+        f.sa = recs[i].ia == COOP_NONE ? uint16_t(COOP_NONE) : slot[idx_of_pos[recs[i].ia]];
+        f.sb = recs[i].ib == COOP_NONE ? uint16_t(COOP_NONE) : slot[idx_of_pos[recs[i].ib]];
+        f.so = slot[i];
+        if (chain_of[i]) {
+            // the previous chain value is the result of the record right before this one
+            const uint16_t prev_pos = recs[i - 1].p;
+            CoopSeg& sg = segs[chain_of[i] - 1];
+            if (i == sg.begin) sg.start_slot = slot[i - 1];
+            if (recs[i].ia == prev_pos) f.sa = uint16_t(COOP_NONE);
+            else f.sb = uint16_t(COOP_NONE);
+        }
+        fwd[i] = f;
+    }
+    return std::max(n_slots, 1u);
 }
 
 static uint64_t fnv1a(const void* data, size_t n) {
@@ -241,6 +321,11 @@ static void upload_schedule(fc_tape* t) {
     sc->hash = h;
     sc->n_clauses = t->host.size();
     if (!build_schedule(t->host, recs, ws, tb, sc->segs)) return;
+    std::vector<CoopFwd> fwd;
+    sc->n_slots = colour_slots(recs, ws, sc->segs, fwd);
+    if (!sc->n_slots) return;
+    if (cudaMalloc(&sc->d_fwd, fwd.size() * sizeof(CoopFwd)) != cudaSuccess) { sc->d_fwd = nullptr; cudaGetLastError(); return; }
+    cudaMemcpy(sc->d_fwd, fwd.data(), fwd.size() * sizeof(CoopFwd), cudaMemcpyHostToDevice);
     if (cudaMalloc(&sc->d_recs, recs.size() * sizeof(CoopRec)) != cudaSuccess) { sc->d_recs = nullptr; cudaGetLastError(); return; }
     if (cudaMalloc(&sc->d_wave_start, ws.size() * 4) != cudaSuccess) { sc->d_wave_start = nullptr; cudaGetLastError(); return; }
     cudaMemcpy(sc->d_recs, recs.data(), recs.size() * sizeof(CoopRec), cudaMemcpyHostToDevice);
@@ -710,22 +795,38 @@ static int32_t bind_vars(const fc_tape* t, const float* values, uint32_t n_value
 
 // Attach the tape's wave schedule to a level-0 launch when the cooperative kernel applies
 // (long tape, few root tiles per SM); returns the grid size or 0.
-static int coop_blocks(fc_ctx* c, const fc_tape* tape, uint64_t n_roots, LevelParams& p) {
+static int coop_blocks(fc_ctx* c, const fc_tape* tape, uint64_t n_roots, LevelParams& p, int dim, int& threads) {
     const Sched* sc = tape->sched.get();
-    if (!sc || !sc->d_recs || !sc->d_wave_start || env_int("FIDGET_B200_NO_COOP", 0)) return 0;
-    size_t smem = coop_smem_bytes(tape->info.n_ops, tape->info.choice_count);
+    if (!sc || !sc->d_recs || !sc->d_fwd || !sc->d_wave_start || env_int("FIDGET_B200_NO_COOP", 0)) return 0;
+    size_t smem = coop_smem_bytes(tape->info.n_ops, tape->info.choice_count, sc->n_slots);
     if (smem > 220 * 1024) return 0;
     // with one lane per tile a warp walks the tape for 32 tiles at once; that only pays when
     // there are enough root tiles to fill the machine several times over
     if (n_roots > uint64_t(c->sm_count) * 32 * 24) return 0;
     p.sched.recs = sc->d_recs;
+    p.sched.fwd = sc->d_fwd;
+    p.sched.n_slots = sc->n_slots;
     p.sched.wave_start = sc->d_wave_start;
     p.sched.n_waves = sc->n_waves;
     p.sched.tail_begin = sc->tail_begin;
     p.sched.tail_end = sc->tail_end;
     p.sched.n_segs = uint32_t(sc->segs.size());
     for (size_t k = 0; k < sc->segs.size(); ++k) p.sched.segs[k] = sc->segs[k];
-    int per_sm = int(std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / (smem + 2048))));
+    // Tiles are latency chains of ~55 barrier steps: what matters is how many ROUNDS of tiles the
+    // launch needs.  Take the fewest CTAs per SM that reach the minimal number of rounds (wider CTAs
+    // shorten a tile), within shared memory (1 KB reserved + ~1.5 KB static per CTA), 2048 threads
+    // and 64 K registers per SM.
+    const int max_by_smem = int(std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / (smem + 2560))));
+    const int cap = std::min(max_by_smem, env_int("FIDGET_B200_COOP_PER_SM", 8));
+    auto rounds = [&](int per_sm) { return (n_roots + uint64_t(c->sm_count) * per_sm - 1) / (uint64_t(c->sm_count) * per_sm); };
+    int per_sm = 1;
+    for (int k = 1; k <= cap; ++k) if (rounds(k) < rounds(per_sm)) per_sm = k;
+    const int regs = (coop_regs_per_thread(dim) + 7) / 8 * 8;
+    threads = COOP_THREADS;
+    while (threads > 64 && (per_sm * threads > 2048 || per_sm * threads * regs > 65536)) threads -= 32;
+    if (env_int("FIDGET_B200_COOP_DEBUG", 0))
+        fprintf(stderr, "coop: %u clauses, %u slots, %zu B smem, %d CTAs/SM x %d threads (%d regs), %llu roots\n", tape->info.n_ops,
+                sc->n_slots, smem, per_sm, threads, regs, (unsigned long long)n_roots);
     return int(std::max<uint64_t>(1, std::min<uint64_t>(n_roots, uint64_t(c->sm_count) * per_sm)));
 }
 
@@ -839,9 +940,10 @@ int32_t fc_render2d(fc_ctx* c, const fc_tape* tape, const fc_render2d_cfg* cfg, 
         }
         bool coop = false;
         if (l == 0) {
-            int cb = coop_blocks(c, tape, n_roots, p);
+            int ct = COOP_THREADS;
+            int cb = coop_blocks(c, tape, n_roots, p, 2, ct);
             if (cb > 0) {
-                CU(launch_interval_root_coop_2d(p, cb, s));
+                CU(launch_interval_root_coop_2d(p, cb, ct, s));
                 coop = true;
             }
         }
@@ -1026,9 +1128,10 @@ int32_t fc_render3d(fc_ctx* c, const fc_tape* tape, const fc_render3d_cfg* cfg, 
         }
         bool coop = false;
         if (l == 0) {
-            int cb = coop_blocks(c, tape, n_roots, p);
+            int ct = COOP_THREADS;
+            int cb = coop_blocks(c, tape, n_roots, p, 3, ct);
             if (cb > 0) {
-                CU(launch_interval_root_coop_3d(p, cb, s));
+                CU(launch_interval_root_coop_3d(p, cb, ct, s));
                 coop = true;
             }
         }

@@ -17,6 +17,7 @@
 // All interpreters keep the tape's VM registers in per-thread local memory
 // (L1-resident, lane-interleaved, so a warp's access to one register is one
 // 128/256-byte line) and read tape clauses with warp-uniform 8-byte loads.
+#include <algorithm>
 #include <cstdio>
 
 #include "kernels.cuh"
@@ -1006,10 +1007,20 @@ void launch_simplify_single(const SimplifyParams& p, cudaStream_t s) { k_simplif
 // k_interval_level_2d (same per-clause arithmetic, same simplify rules).
 namespace fdev {
 
-size_t coop_smem_bytes(uint32_t n_ops, uint32_t n_choices) {
-    return size_t(n_ops) * 8 + size_t((n_choices + 15) / 16 + 1) * 4 + 16;
+// shared memory of one root tile: forward values by slot, overlaid by the reverse pass's
+// last_use words (one per clause; bits 16.. hold the emit code), then the 2-bit choices
+size_t coop_smem_bytes(uint32_t n_ops, uint32_t n_choices, uint32_t n_slots) {
+    return std::max(size_t(n_slots) * 8, size_t(n_ops) * 4) + size_t((n_choices + 15) / 16 + 1) * 4 + 16;
 }
 
+struct Fwd {
+    uint32_t x, y, sa, sb, so, cidx;
+    __device__ __forceinline__ explicit Fwd(const uint4 q)
+        : x(q.x), y(q.y), sa(q.z & 0xffffu), sb(q.z >> 16), so(q.w & 0xffffu), cidx(q.w >> 16) {}
+};
+__device__ __forceinline__ Fwd load_fwd(const CoopFwd* f, uint32_t i) {
+    return Fwd(__ldg(reinterpret_cast<const uint4*>(f) + i));
+}
 struct Rec {
     uint32_t x, y, ia, ib, p, cidx;
     __device__ __forceinline__ explicit Rec(const uint4 q)
@@ -1025,18 +1036,21 @@ k_interval_root_coop(const __grid_constant__ LevelParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t n = p.root_tape.n_ops, nch = p.root_tape.n_choices;
     const uint32_t cw = (nch + 15u) / 16u + 1u;
-    itv* vals = reinterpret_cast<itv*>(smem_raw);
-    uint32_t* chs = reinterpret_cast<uint32_t*>(smem_raw + size_t(n) * 8);
-    uint32_t* last_use = reinterpret_cast<uint32_t*>(smem_raw);   // overlays vals after the forward pass
-    uint8_t* emit = smem_raw + size_t(n) * 4;
+    itv* vals = reinterpret_cast<itv*>(smem_raw);                 // forward: values by slot
+    const size_t data_bytes = max(size_t(p.sched.n_slots) * 8, size_t(n) * 4);
+    uint32_t* chs = reinterpret_cast<uint32_t*>(smem_raw + data_bytes);
+    // reverse: one word per clause, overlaying vals: bits 0..15 = 1 + position of the last live
+    // reader (0: dead), bits 16.. = emit code
+    uint32_t* last_use = reinterpret_cast<uint32_t*>(smem_raw);
     __shared__ itv s_res;
     __shared__ uint32_t s_tile, s_nonboth, s_warp_tot[COOP_THREADS / 32], s_ref, s_nch;
     __shared__ unsigned long long s_base;
-    __shared__ float s_agg_lo[COOP_THREADS], s_agg_hi[COOP_THREADS];
-    __shared__ uint8_t s_agg_f[COOP_THREADS], s_agg_u[COOP_THREADS];
+    __shared__ float s_agg_lo[COOP_THREADS / 32], s_agg_hi[COOP_THREADS / 32];
+    __shared__ uint8_t s_agg_f[COOP_THREADS / 32], s_agg_u[COOP_THREADS / 32];
 
-    const uint32_t tid = threadIdx.x, T = p.tile;
+    const uint32_t tid = threadIdx.x, T = p.tile, NT = blockDim.x;   // NT <= COOP_THREADS, a multiple of 32
     const CoopRec* __restrict__ recs = p.sched.recs;
+    const CoopFwd* __restrict__ fwd = p.sched.fwd;
     const uint32_t* __restrict__ ws = p.sched.wave_start;
     const uint32_t n_roots = p.roots_x * p.roots_y * (DIM == 3 ? p.roots_z : 1u);
     const uint2* __restrict__ tape = p.root_tape.ptr;
@@ -1049,7 +1063,7 @@ k_interval_root_coop(const __grid_constant__ LevelParams p) {
             s_nch = 0;
             s_res = iv_nan();
         }
-        for (uint32_t i = tid; i < cw; i += COOP_THREADS) chs[i] = 0;
+        for (uint32_t i = tid; i < cw; i += NT) chs[i] = 0;
         __syncthreads();
         const uint32_t tile = s_tile;
         if (tile >= n_roots) break;
@@ -1063,7 +1077,7 @@ k_interval_root_coop(const __grid_constant__ LevelParams p) {
             if (c != 3u) s_nonboth = 1u;
         };
         auto get_choice = [&](uint32_t cidx) { return (chs[cidx >> 4] >> ((cidx & 15u) * 2u)) & 3u; };
-        auto exec = [&](const Rec& rc, itv sl, itv sr) -> itv {
+        auto exec = [&](const Fwd& rc, itv sl, itv sr) -> itv {
             Dec d(rc.x);
             float imm = __uint_as_float(rc.y);
             itv a = d.form == F_IR ? iv1(imm) : sl;
@@ -1104,16 +1118,17 @@ k_interval_root_coop(const __grid_constant__ LevelParams p) {
                 }
             };
             advance();
-            uint4 q = (w < n_waves) ? __ldg(reinterpret_cast<const uint4*>(recs) + i) : make_uint4(0, 0, 0, 0);
+            uint4 q = (w < n_waves) ? __ldg(reinterpret_cast<const uint4*>(fwd) + i) : make_uint4(0, 0, 0, 0);
             uint32_t cur_w = 0;
             while (cur_w < n_waves) {
                 // run everything this thread owns in wave cur_w
                 while (w == cur_w) {
-                    const Rec rc(q);
-                    i += COOP_THREADS;
+                    const Fwd rc(q);
+                    i += NT;
                     advance();
-                    if (w < n_waves) q = __ldg(reinterpret_cast<const uint4*>(recs) + i);
-                    vals[rc.p] = exec(rc, ld(rc.ia), ld(rc.ib));
+                    if (w < n_waves) q = __ldg(reinterpret_cast<const uint4*>(fwd) + i);
+                    const itv r = exec(rc, ld(rc.sa), ld(rc.sb));
+                    if (rc.so != COOP_NONE) vals[rc.so] = r;
                 }
                 __syncthreads();
                 ++cur_w;
@@ -1125,25 +1140,27 @@ k_interval_root_coop(const __grid_constant__ LevelParams p) {
             const uint32_t b = p.sched.segs[sgi].begin, e = p.sched.segs[sgi].end;
             if (!p.sched.segs[sgi].chain) {
                 if (tid == 0) {
-                    uint32_t last_p = COOP_NONE;
+                    uint32_t last_s = COOP_NONE;
                     itv last_r = iv_nan();
                     for (uint32_t i = b; i < e; ++i) {
-                        const Rec rc = load_rec(recs, i);
-                        itv sl = rc.ia == last_p ? last_r : ld(rc.ia);
-                        itv sr = rc.ib == last_p ? last_r : ld(rc.ib);
-                        itv r = exec(rc, sl, sr);
-                        vals[rc.p] = r;
-                        last_p = rc.p;
+                        const Fwd rc = load_fwd(fwd, i);
+                        const itv sl = (rc.sa == last_s && last_s != COOP_NONE) ? last_r : ld(rc.sa);
+                        const itv sr = (rc.sb == last_s && last_s != COOP_NONE) ? last_r : ld(rc.sb);
+                        const itv r = exec(rc, sl, sr);
+                        if (rc.so != COOP_NONE) vals[rc.so] = r;
+                        last_s = rc.so;
                         last_r = r;
                     }
                 }
             } else {
                 // m_i = OP(m_{i-1}, s_i): prefix scan over the sides
-                const uint32_t m = e - b, ch = (m + COOP_THREADS - 1) / COOP_THREADS;
+                const uint32_t m = e - b, ch = (m + NT - 1) / NT;
                 const uint32_t c0 = min(e, b + tid * ch), c1 = min(e, c0 + ch);
-                const Rec first = load_rec(recs, b);
+                // (forward view: the operand that is the previous chain value is marked COOP_NONE,
+                //  the value the chain starts from sits in segs[].start_slot)
+                const Fwd first = load_fwd(fwd, b);
                 const bool is_min = (Dec(first.x).op == OP_MIN);
-                const uint32_t prev_first = load_rec(recs, b - 1).p;
+                const uint32_t start_slot = p.sched.segs[sgi].start_slot;
                 auto comb = [&](float& lo, float& hi, uint32_t& f, itv s) {
                     f |= uint32_t(iv_has_nan(s));
                     lo = is_min ? fminf(lo, s.x) : fmaxf(lo, s.x);
@@ -1152,13 +1169,9 @@ k_interval_root_coop(const __grid_constant__ LevelParams p) {
                 const float ident = is_min ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);
                 float alo = ident, ahi = ident;
                 uint32_t af = 0;
-                {
-                    uint32_t prev = c0 > b ? load_rec(recs, c0 - 1).p : prev_first;
-                    for (uint32_t i = c0; i < c1; ++i) {
-                        const Rec rc = load_rec(recs, i);
-                        comb(alo, ahi, af, vals[rc.ia == prev ? rc.ib : rc.ia]);
-                        prev = rc.p;
-                    }
+                for (uint32_t i = c0; i < c1; ++i) {
+                    const Fwd rc = load_fwd(fwd, i);
+                    comb(alo, ahi, af, vals[rc.sa == COOP_NONE ? rc.sb : rc.sa]);
                 }
                 // exclusive block scan of the per-thread aggregates (warp shuffles + one smem hop)
                 float xlo = alo, xhi = ahi;
@@ -1181,7 +1194,7 @@ k_interval_root_coop(const __grid_constant__ LevelParams p) {
                 if (ln == 0u) { elo = ident; ehi = ident; ef = 0; }
                 __syncthreads();
                 if (c0 < c1) {
-                    const itv start = vals[prev_first];
+                    const itv start = vals[start_slot];
                     float lo = start.x, hi = start.y;
                     uint32_t f = uint32_t(iv_has_nan(start));
                     for (uint32_t k = 0; k < wp; ++k) {
@@ -1192,19 +1205,17 @@ k_interval_root_coop(const __grid_constant__ LevelParams p) {
                     f |= ef;
                     lo = is_min ? fminf(lo, elo) : fmaxf(lo, elo);
                     hi = is_min ? fminf(hi, ehi) : fmaxf(hi, ehi);
-                    uint32_t prev = c0 > b ? load_rec(recs, c0 - 1).p : prev_first;
                     for (uint32_t i = c0; i < c1; ++i) {
-                        const Rec rc = load_rec(recs, i);
-                        const bool prev_is_lhs = (rc.ia == prev);
-                        const itv s = vals[prev_is_lhs ? rc.ib : rc.ia];
+                        const Fwd rc = load_fwd(fwd, i);
+                        const bool prev_is_lhs = (rc.sa == COOP_NONE);
+                        const itv s = vals[prev_is_lhs ? rc.sb : rc.sa];
                         const itv mprev = f ? iv_nan() : iv(lo, hi);
                         uint32_t c;
                         const itv r = prev_is_lhs ? iv_choice_op(is_min ? OP_MIN : OP_MAX, mprev, s, c)
                                                   : iv_choice_op(is_min ? OP_MIN : OP_MAX, s, mprev, c);
                         comb(lo, hi, f, s);
                         put_choice(rc.cidx, c);
-                        vals[rc.p] = r;
-                        prev = rc.p;
+                        if (rc.so != COOP_NONE) vals[rc.so] = r;
                     }
                 }
             }
@@ -1217,7 +1228,7 @@ k_interval_root_coop(const __grid_constant__ LevelParams p) {
         const bool amb = !fill_in && !fill_out;
         if (DIM == 3 && fill_in) {   // voxel.rs:310-317
             const unsigned long long key = (unsigned long long)(cz + T + 1u) << 32;
-            for (uint32_t q = tid; q < T * T; q += COOP_THREADS) {
+            for (uint32_t q = tid; q < T * T; q += NT) {
                 const uint32_t x = cx + q % T, y = cy + q / T;
                 if (x < p.width && y < p.height) atomicMax(&p.heightmap[size_t(y) * p.width + x], key);
             }
@@ -1245,7 +1256,7 @@ k_interval_root_coop(const __grid_constant__ LevelParams p) {
         TapeRef child = p.root_tape;
         if (s_nonboth) {   // uniform: written before the last barrier
             // ---- R1: reverse liveness; last_use[v] = 1 + position of the last live clause reading v ----
-            for (uint32_t i = tid; i < n; i += COOP_THREADS) last_use[i] = 0;
+            for (uint32_t i = tid; i < n; i += NT) last_use[i] = 0;
             __syncthreads();
             auto r1 = [&](const Rec& rc) {
                 Dec d(rc.x);
@@ -1267,7 +1278,7 @@ k_interval_root_coop(const __grid_constant__ LevelParams p) {
                         for (uint32_t i = e; i > b; --i) r1(load_rec(recs, i - 1));
                 } else {
                     // live_i = ext_i | (uses_prev_{i+1} & live_{i+1}), suffix scan over the run
-                    const uint32_t m = e - b, ch = (m + COOP_THREADS - 1) / COOP_THREADS;
+                    const uint32_t m = e - b, ch = (m + NT - 1) / NT;
                     const uint32_t c0 = min(e, b + tid * ch), c1 = min(e, c0 + ch);
                     const uint32_t prev_first = load_rec(recs, b - 1).p;
                     auto uses_prev = [&](const Rec& rc, uint32_t prevp) {
@@ -1299,7 +1310,7 @@ k_interval_root_coop(const __grid_constant__ LevelParams p) {
                     __syncthreads();
                     if (c0 < c1) {
                         uint32_t y = 0;   // (uses_prev & live) of the element right after this chunk
-                        for (uint32_t k = COOP_THREADS / 32; k > wp + 1u; --k) y = s_agg_f[k - 1] | (s_agg_u[k - 1] & y);
+                        for (uint32_t k = (NT >> 5); k > wp + 1u; --k) y = s_agg_f[k - 1] | (s_agg_u[k - 1] & y);
                         y = eO | (eU & y);
                         for (uint32_t i = c1; i > c0; --i) {
                             const Rec rc = load_rec(recs, i - 1);
@@ -1321,17 +1332,17 @@ k_interval_root_coop(const __grid_constant__ LevelParams p) {
             }
             for (uint32_t w = p.sched.n_waves; w > 0; --w) {
                 const uint32_t e = ws[w];
-                for (uint32_t i = ws[w - 1] + tid; i < e; i += COOP_THREADS) r1(load_rec(recs, i));
+                for (uint32_t i = ws[w - 1] + tid; i < e; i += NT) r1(load_rec(recs, i));
                 __syncthreads();
             }
             // ---- R2a: what each clause turns into ----
             // 0 none, 1 as is, 7 as is (choice kept), 2/3 copy lhs real/alias, 4/5 copy rhs real/alias, 6 copy imm
-            for (uint32_t i = tid; i < p.sched.tail_end; i += COOP_THREADS) {
+            for (uint32_t i = tid; i < p.sched.tail_end; i += NT) {
                 const Rec rc = load_rec(recs, i);
                 Dec d(rc.x);
                 const uint32_t pos = rc.p;
                 uint32_t code;
-                if (d.op != OP_OUTPUT && last_use[pos] == 0u) code = 0;
+                if (d.op != OP_OUTPUT && (last_use[pos] & 0xffffu) == 0u) code = 0;
                 else if (d.op >= OP_MIN) {
                     uint32_t c = get_choice(rc.cidx);
                     if (c == 3u) code = 7;
@@ -1340,22 +1351,22 @@ k_interval_root_coop(const __grid_constant__ LevelParams p) {
                         const bool use_rhs = (c == 2u);
                         const uint32_t src_reg = use_rhs ? d.rhs : d.lhs, src_def = use_rhs ? rc.ib : rc.ia;
                         if (src_reg == d.out) code = 0;
-                        else code = (use_rhs ? 4u : 2u) + (last_use[src_def] > pos + 1u ? 0u : 1u);
+                        else code = (use_rhs ? 4u : 2u) + ((last_use[src_def] & 0xffffu) > pos + 1u ? 0u : 1u);
                     }
                 } else if (d.op == OP_COPY && d.form != F_RI) {
                     if (d.lhs == d.out) code = 0;
                     else if (d.form == F_ALIAS) code = 3;
-                    else code = last_use[rc.ia] > pos + 1u ? 2u : 3u;
+                    else code = (last_use[rc.ia] & 0xffffu) > pos + 1u ? 2u : 3u;
                 } else code = 1;
-                emit[pos] = uint8_t(code);
+                last_use[pos] = (last_use[pos] & 0xffffu) | (code << 16);   // only this thread writes word `pos`
             }
             __syncthreads();
             // ---- R2b: scan in tape order, then write the compacted child ----
-            const uint32_t chunk = (n + COOP_THREADS - 1) / COOP_THREADS;
+            const uint32_t chunk = (n + NT - 1) / NT;
             const uint32_t b0 = min(n, tid * chunk), b1 = min(n, b0 + chunk);
             uint32_t my_dev = 0, my_ref = 0, my_nch = 0;
             for (uint32_t q = b0; q < b1; ++q) {
-                uint32_t c = emit[q];
+                uint32_t c = last_use[q] >> 16;
                 my_dev += (c != 0u);
                 my_ref += (c != 0u && c != 3u && c != 5u);
                 my_nch += (c == 7u);
@@ -1370,7 +1381,7 @@ k_interval_root_coop(const __grid_constant__ LevelParams p) {
             if (my_nch) atomicAdd(&s_nch, my_nch);
             __syncthreads();
             uint32_t warp_off = 0, n_dev = 0;
-            for (uint32_t k = 0; k < COOP_THREADS / 32; ++k) {
+            for (uint32_t k = 0; k < (NT >> 5); ++k) {
                 if (k < (tid >> 5)) warp_off += s_warp_tot[k];
                 n_dev += s_warp_tot[k];
             }
@@ -1390,7 +1401,7 @@ k_interval_root_coop(const __grid_constant__ LevelParams p) {
                 if (base != ~0ull) {
                     uint2* dst = p.arena + base + warp_off + (incl - my_dev);
                     for (uint32_t q = b0; q < b1; ++q) {
-                        uint32_t c = emit[q];
+                        uint32_t c = last_use[q] >> 16;
                         if (!c) continue;
                         uint2 w = __ldg(tape + q);
                         if (c != 1u && c != 7u) {
@@ -1428,19 +1439,29 @@ k_interval_root_coop(const __grid_constant__ LevelParams p) {
 }
 
 template <int DIM>
-static cudaError_t launch_coop(const LevelParams& p, int blocks, cudaStream_t s) {
-    size_t smem = coop_smem_bytes(p.root_tape.n_ops, p.root_tape.n_choices);
+static cudaError_t launch_coop(const LevelParams& p, int blocks, int threads, cudaStream_t s) {
+    size_t smem = coop_smem_bytes(p.root_tape.n_ops, p.root_tape.n_choices, p.sched.n_slots);
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(k_interval_root_coop<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    k_interval_root_coop<DIM><<<blocks, COOP_THREADS, smem, s>>>(p);
+    k_interval_root_coop<DIM><<<blocks, threads, smem, s>>>(p);
     return cudaGetLastError();
 }
-cudaError_t launch_interval_root_coop_2d(const LevelParams& p, int blocks, cudaStream_t s) { return launch_coop<2>(p, blocks, s); }
-cudaError_t launch_interval_root_coop_3d(const LevelParams& p, int blocks, cudaStream_t s) { return launch_coop<3>(p, blocks, s); }
+int coop_regs_per_thread(int dim) {
+    static int regs[2] = {0, 0};
+    int& r = regs[dim == 3];
+    if (!r) {
+        cudaFuncAttributes a{};
+        cudaError_t e = dim == 3 ? cudaFuncGetAttributes(&a, k_interval_root_coop<3>) : cudaFuncGetAttributes(&a, k_interval_root_coop<2>);
+        r = e == cudaSuccess ? a.numRegs : 64;
+    }
+    return r;
+}
+cudaError_t launch_interval_root_coop_2d(const LevelParams& p, int blocks, int threads, cudaStream_t s) { return launch_coop<2>(p, blocks, threads, s); }
+cudaError_t launch_interval_root_coop_3d(const LevelParams& p, int blocks, int threads, cudaStream_t s) { return launch_coop<3>(p, blocks, threads, s); }
 
 }  // namespace fdev
 

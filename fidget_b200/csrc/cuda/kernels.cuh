@@ -68,9 +68,21 @@ struct CoopRec {
 // previous clause's result with a value computed before the run) are
 // evaluated with a block-wide prefix scan: min/max of intervals is exactly
 // associative, and the choices follow from the prefix values.
-struct CoopSeg { uint32_t begin, end, chain; };
+struct CoopSeg { uint32_t begin, end, chain, start_slot; };   // start_slot: slot of the value a chain starts from
+// The forward pass addresses values by SLOT, not by defining clause: the host colours the
+// values of the schedule so that a slot is reused once every reader of its value has run
+// (prospero: 6363 values -> ~2700 slots), which is what lets seven root tiles share an SM.
+// A chain value whose only reader is the next clause of the same chain gets no slot at all.
+struct CoopFwd {
+    uint32_t x, y;        // the device clause
+    uint16_t sa, sb;      // slots of the lhs / rhs register operands (COOP_NONE: immediate/unused)
+    uint16_t so;          // slot of the result (COOP_NONE: not stored)
+    uint16_t cidx;        // choice index (choice clauses only)
+};
 constexpr int COOP_MAX_SEGS = 16;
 struct CoopSched {
+    const CoopFwd* fwd;           // forward view of the same records (slots instead of positions)
+    uint32_t n_slots;
     const CoopRec* recs;
     const uint32_t* wave_start;   // [n_waves + 1] offsets into recs
     uint32_t n_waves;
@@ -207,9 +219,10 @@ void launch_normals_3d(const NormalParams& p, cudaStream_t s);
 void launch_merge_slabs(const void* const* d_slabs, uint32_t n_slabs, uint32_t n_pixels, uint32_t depth, void* out,
                         cudaStream_t s);
 void launch_interval_level_2d(const LevelParams& p, int blocks, cudaStream_t s);
-size_t coop_smem_bytes(uint32_t n_ops, uint32_t n_choices);
-cudaError_t launch_interval_root_coop_2d(const LevelParams& p, int blocks, cudaStream_t s);
-cudaError_t launch_interval_root_coop_3d(const LevelParams& p, int blocks, cudaStream_t s);
+int coop_regs_per_thread(int dim);
+size_t coop_smem_bytes(uint32_t n_ops, uint32_t n_choices, uint32_t n_slots);
+cudaError_t launch_interval_root_coop_2d(const LevelParams& p, int blocks, int threads, cudaStream_t s);
+cudaError_t launch_interval_root_coop_3d(const LevelParams& p, int blocks, int threads, cudaStream_t s);
 void launch_pixels_2d(const PixelParams& p, int blocks, cudaStream_t s);
 void launch_fill_2d(const FillParams& p, int blocks, cudaStream_t s);
 
