@@ -815,18 +815,27 @@ static int coop_blocks(fc_ctx* c, const fc_tape* tape, uint64_t n_roots, LevelPa
     // Tiles are latency chains of ~55 barrier steps: what matters is how many ROUNDS of tiles the
     // launch needs.  Take the fewest CTAs per SM that reach the minimal number of rounds (wider CTAs
     // shorten a tile), within shared memory (1 KB reserved + ~1.5 KB static per CTA), 2048 threads
-    // and 64 K registers per SM.
+    // and the register file.
     const int max_by_smem = int(std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / (smem + 2560))));
     const int cap = std::min(max_by_smem, env_int("FIDGET_B200_COOP_PER_SM", 8));
     auto rounds = [&](int per_sm) { return (n_roots + uint64_t(c->sm_count) * per_sm - 1) / (uint64_t(c->sm_count) * per_sm); };
     int per_sm = 1;
     for (int k = 1; k <= cap; ++k) if (rounds(k) < rounds(per_sm)) per_sm = k;
-    const int regs = (coop_regs_per_thread(dim) + 7) / 8 * 8;
-    threads = COOP_THREADS;
-    while (threads > 64 && (per_sm * threads > 2048 || per_sm * threads * regs > 65536)) threads -= 32;
+    // widest CTA for which the runtime really keeps per_sm of them resident (register granularity
+    // makes 7 x 224 threads x 40 registers NOT fit although 7 * 224 * 40 < 64 K)
+    static struct { size_t smem; int per_sm, threads; } memo[2] = {};
+    auto& mm = memo[dim == 3];
+    if (mm.threads == 0 || mm.smem != smem || mm.per_sm != per_sm) {
+        int t = COOP_THREADS;
+        while (t > 64 && coop_occupancy(dim, t, smem) < per_sm) t -= 32;
+        mm = {smem, per_sm, t};
+    }
+    threads = mm.threads;
+    threads = env_int("FIDGET_B200_COOP_THREADS", threads);
     if (env_int("FIDGET_B200_COOP_DEBUG", 0))
-        fprintf(stderr, "coop: %u clauses, %u slots, %zu B smem, %d CTAs/SM x %d threads (%d regs), %llu roots\n", tape->info.n_ops,
-                sc->n_slots, smem, per_sm, threads, regs, (unsigned long long)n_roots);
+        fprintf(stderr, "coop: %u clauses, %u slots, %zu B smem, %d CTAs/SM x %d threads (%d regs), %llu roots, occupancy %d CTAs/SM\n",
+                tape->info.n_ops, sc->n_slots, smem, per_sm, threads, coop_regs_per_thread(dim), (unsigned long long)n_roots,
+                coop_occupancy(dim, threads, smem));
     return int(std::max<uint64_t>(1, std::min<uint64_t>(n_roots, uint64_t(c->sm_count) * per_sm)));
 }
 

@@ -1445,10 +1445,18 @@ static cudaError_t launch_coop(const LevelParams& p, int blocks, int threads, cu
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(k_interval_root_coop<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) return e;
+        // many small CTAs per SM: ask for the largest shared-memory carve-out
+        cudaFuncSetAttribute(k_interval_root_coop<DIM>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured = smem;
     }
     k_interval_root_coop<DIM><<<blocks, threads, smem, s>>>(p);
     return cudaGetLastError();
+}
+int coop_occupancy(int dim, int threads, size_t smem) {
+    int n = 0;
+    if (dim == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_interval_root_coop<3>, threads, smem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_interval_root_coop<2>, threads, smem);
+    return n;
 }
 int coop_regs_per_thread(int dim) {
     static int regs[2] = {0, 0};

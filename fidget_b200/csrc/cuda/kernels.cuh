@@ -220,6 +220,7 @@ void launch_merge_slabs(const void* const* d_slabs, uint32_t n_slabs, uint32_t n
                         cudaStream_t s);
 void launch_interval_level_2d(const LevelParams& p, int blocks, cudaStream_t s);
 int coop_regs_per_thread(int dim);
+int coop_occupancy(int dim, int threads, size_t smem);
 size_t coop_smem_bytes(uint32_t n_ops, uint32_t n_choices, uint32_t n_slots);
 cudaError_t launch_interval_root_coop_2d(const LevelParams& p, int blocks, int threads, cudaStream_t s);
 cudaError_t launch_interval_root_coop_3d(const LevelParams& p, int blocks, int threads, cudaStream_t s);
