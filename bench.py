@@ -5,9 +5,12 @@ A step = one pass of the hot path over one frame of synthetic input:
   N = 1 : models/prospero.vm, 2D render 4096x4096 (BASELINE.json configs[1]):
           interval levels [128,32,8] with on-device tape simplification, fill,
           bulk f32 over the surviving leaf tiles.
-  N > 1 : the same frame sharded by bands of root-tile rows (one band per
-          rank, no data-path collective while rendering) followed by ONE NCCL
-          all-gather of the bands; scaling = "strong" (total work fixed).
+  N > 1 : default ("weak"): one 4096x4096 Z slice of the same model per GPU (rank r renders the
+          voxel layer z_r of a 4096^3 grid), no collective on the data path -- the slices are
+          independent units; a step = N slices, value = N * 4096^2 / max-over-ranks time.
+          --scaling strong: ONE frame sharded by bands of root-tile rows + ONE NCCL all-gather
+          of the bands (total work fixed).  A 0.32 ms frame is a chain of four latency-bound
+          launches, so bands do not shorten it (measured: profiles/r01_bench_n2.json).
 
   python bench.py --gpus N --steps K --warmup W           # CUDA arm
   python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port, all host threads)
@@ -128,7 +131,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "Mvoxels/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": args.scaling if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"models/{MODEL} 2D render {SIZE}x{SIZE}, tile sizes [128,32,8], identity camera"},
         "cpu_baseline": {"value": v, "unit": "Mvoxels/s", "cores": threads, "kind": "port",
                          "sample": f"each step = one full {SIZE}x{SIZE} frame, {threads} host threads; the Rust "
@@ -146,6 +149,8 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = one Z slice per GPU (default), strong = one frame in bands + all-gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -174,17 +179,20 @@ def main():
     from fidget_b200.shard import band_rows
     T0 = 128
     n_rows = SIZE // T0
-    rows = band_rows(rank, world, SIZE, T0) if world > 1 else (0, 0)
-    cfg = fb.RenderConfig2D(SIZE, SIZE, root_rows=rows)
+    strong = world > 1 and args.scaling == "strong"
+    rows = band_rows(rank, world, SIZE, T0) if strong else (0, 0)
+    # weak scaling: rank r renders voxel layer z_r of the SIZE^3 grid around z = 0 (region.rs:87-108: one voxel = 2/SIZE)
+    z_slice = (rank - (world - 1) / 2.0) * (2.0 / SIZE) if world > 1 and not strong else 0.0
+    cfg = fb.RenderConfig2D(SIZE, SIZE, root_rows=rows, z=z_slice)
     image = torch.zeros((SIZE, SIZE), dtype=torch.float32, device=dev)
-    gathered = torch.empty_like(image) if world > 1 else None
+    gathered = torch.empty_like(image) if strong else None
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     from fidget_b200.shard import render2d_bands
     full_cfg = fb.RenderConfig2D(SIZE, SIZE)
 
     def step():
-        if world > 1:
+        if strong:
             render2d_bands(shape, full_cfg, image, gathered)   # band render + ONE all-gather
         else:
             fb.render2d(shape, cfg, out=image, asynchronous=True)
@@ -217,10 +225,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    value = SIZE * SIZE / (ms_per_step * 1e-3) / 1e6
+    frames_per_step = 1 if (world == 1 or strong) else world       # weak: every rank renders its own slice
+    value = frames_per_step * SIZE * SIZE / (ms_per_step * 1e-3) / 1e6
 
     # ---- per-kernel timing of one step (CUDA events inside the library) ----
-    tcfg = fb.RenderConfig2D(SIZE, SIZE, root_rows=rows, timing=True)
+    tcfg = fb.RenderConfig2D(SIZE, SIZE, root_rows=rows, z=z_slice, timing=True)
     stage = np.zeros(16)
     reps = 5
     stats = None
@@ -232,7 +241,7 @@ def main():
     names = {0: "k_interval_root_coop_2d[L0,128px]", 1: "k_interval_level<2>[L1,32px]",
              2: "k_interval_level<2>[L2,8px]", 8: "k_fill_2d (x3)", 9: "k_pixels_2d"}
     dom = max(names, key=lambda k: stage[k])
-    frac_rows = (rows[1] - rows[0]) / n_rows if world > 1 else 1.0
+    frac_rows = (rows[1] - rows[0]) / n_rows if strong else 1.0
     # units decided by one launch of the dominant kernel (DESIGN.md "Measurement")
     if dom in (0, 1, 2):
         tile = [128, 32, 8][dom]
@@ -279,8 +288,9 @@ def main():
     if world > 1:
         dist.all_reduce(et, op=dist.ReduceOp.MAX)
     e2e_dt = float(et.item())
-    e2e = {"value": SIZE * SIZE * (1.0 if world == 1 else 1.0) / e2e_dt / 1e6, "unit": "Mvoxels/s",
-           "h2d_bytes_per_step": int(bc.words.nbytes), "d2h_bytes_per_step": int(SIZE * SIZE * 4 * frac_rows),
+    e2e = {"value": frames_per_step * SIZE * SIZE / e2e_dt / 1e6, "unit": "Mvoxels/s",
+           "h2d_bytes_per_step": int(bc.words.nbytes) * frames_per_step,
+           "d2h_bytes_per_step": int(SIZE * SIZE * 4 * frac_rows) * frames_per_step,
            "ms_per_step": e2e_dt * 1e3,
            "note": "fc_tape_create from host bytecode + fc_render2d into a pinned host image, wall clock"}
 
@@ -288,14 +298,17 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "Mvoxels/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"models/{MODEL} 2D render {SIZE}x{SIZE}, tile sizes [128,32,8] (reference VM "
                                    "defaults), identity camera, pixel_perfect=false",
-                       "parallelism": "single GPU" if world == 1 else f"{world} bands of root-tile rows + 1 all-gather",
+                       "parallelism": "single GPU" if world == 1 else (
+                           f"{world} bands of root-tile rows of ONE frame + 1 all-gather" if strong else
+                           f"{world} independent {SIZE}x{SIZE} Z slices (layers z_r of a {SIZE}^3 grid), one per GPU, "
+                           "no data-path collective; value = all slices / max-over-ranks time"),
                        "l2": "flushed between steps by a 512 MiB fill outside the event-timed regions"},
             "clocks": clocks.summary(),
             "e2e": e2e,
-            "gpu_launches": int(stats["kernel_launches"]) * args.steps,
+            "gpu_launches": int(stats["kernel_launches"]) * args.steps * frames_per_step,
             "roofline": roofline,
         }
         if not args.no_cpu_baseline:
