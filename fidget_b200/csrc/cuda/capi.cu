@@ -94,6 +94,7 @@ struct fc_ctx {
     DevBuf fx_in, fx_out, fx_tmp, fx_tables;  // effects: staged host images, intermediate maps, SSAO tables
     std::vector<cudaEvent_t> events;
     std::mutex mu;
+    struct { size_t smem; int per_sm, threads; } coop_memo[2] = {};   // level-0 launch shape per DIM (occupancy query cached)
     std::shared_ptr<struct Sched> sched_cache[4];
     unsigned sched_next = 0;
 };
@@ -823,8 +824,7 @@ static int coop_blocks(fc_ctx* c, const fc_tape* tape, uint64_t n_roots, LevelPa
     for (int k = 1; k <= cap; ++k) if (rounds(k) < rounds(per_sm)) per_sm = k;
     // widest CTA for which the runtime really keeps per_sm of them resident (register granularity
     // makes 7 x 224 threads x 40 registers NOT fit although 7 * 224 * 40 < 64 K)
-    static struct { size_t smem; int per_sm, threads; } memo[2] = {};
-    auto& mm = memo[dim == 3];
+    auto& mm = c->coop_memo[dim == 3];
     if (mm.threads == 0 || mm.smem != smem || mm.per_sm != per_sm) {
         int t = COOP_THREADS;
         while (t > 64 && coop_occupancy(dim, t, smem) < per_sm) t -= 32;
