@@ -94,6 +94,12 @@ struct fc_ctx {
     DevBuf fx_in, fx_out, fx_tmp, fx_tables;  // effects: staged host images, intermediate maps, SSAO tables
     std::vector<cudaEvent_t> events;
     std::mutex mu;
+    // tape uploads: released device buffers are reused (no cudaMalloc / cudaFree per tape) and the
+    // clauses go through a pinned staging buffer with a stream-ordered copy (no host synchronisation)
+    std::vector<std::pair<size_t, uint2*>> tape_pool;
+    void* stage = nullptr;
+    size_t stage_cap = 0;
+    cudaEvent_t stage_ev = nullptr;
     struct { size_t smem; int per_sm, threads; } coop_memo[2] = {};   // level-0 launch shape per DIM (occupancy query cached)
     std::shared_ptr<struct Sched> sched_cache[4];
     unsigned sched_next = 0;
@@ -103,6 +109,8 @@ struct fc_tape {
     fc_ctx* ctx = nullptr;
     std::atomic<int> refs{1};
     uint2* dev = nullptr;
+    size_t dev_cap = 0;       // bytes behind `dev` (a pooled buffer may be larger than the tape)
+    bool pooled_ok = true;    // false for tapes whose buffer is not a plain cudaMalloc of their own
     std::vector<uint2> host;  // copy of the device clauses
     fc_tape_info info{};
     int ax[3] = {-1, -1, -1};  // input slots of X, Y, Z
@@ -298,17 +306,20 @@ static uint32_t colour_slots(const std::vector<CoopRec>& recs, const std::vector
     return std::max(n_slots, 1u);
 }
 
-static uint64_t fnv1a(const void* data, size_t n) {
-    const unsigned char* p = static_cast<const unsigned char*>(data);
+// FNV-1a over 64-bit words (one device clause per step)
+static uint64_t fnv1a(const uint2* cl, size_t n) {
     uint64_t h = 1469598103934665603ull;
-    for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    for (size_t i = 0; i < n; ++i) {
+        h ^= uint64_t(cl[i].x) | uint64_t(cl[i].y) << 32;
+        h *= 1099511628211ull;
+    }
     return h;
 }
 
 static void upload_schedule(fc_tape* t) {
     fc_ctx* c = t->ctx;
     if (t->host.size() < 64) return;   // the cooperative kernel is never used for short tapes
-    const uint64_t h = fnv1a(t->host.data(), t->host.size() * sizeof(uint2));
+    const uint64_t h = fnv1a(t->host.data(), t->host.size());
     {
         std::lock_guard<std::mutex> g(c->mu);
         for (auto& sp : c->sched_cache)
@@ -466,6 +477,9 @@ void fc_ctx_destroy(fc_ctx* c) {
     c->fx_out.release();
     c->fx_tmp.release();
     c->fx_tables.release();
+    for (auto& pb : c->tape_pool) cudaFree(pb.second);
+    if (c->stage) cudaFreeHost(c->stage);
+    if (c->stage_ev) cudaEventDestroy(c->stage_ev);
     for (auto ev : c->events) cudaEventDestroy(ev);
     for (auto e : c->ev_fork) if (e) cudaEventDestroy(e);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -476,7 +490,12 @@ void fc_ctx_destroy(fc_ctx* c) {
 
 int32_t fc_ctx_set_stream(fc_ctx* c, void* s, int32_t use_own) {
     if (!c) return fail(FC_ERR_INVALID, "null ctx");
-    c->stream = use_own ? c->own_stream : static_cast<cudaStream_t>(s);
+    cudaStream_t ns = use_own ? c->own_stream : static_cast<cudaStream_t>(s);
+    if (ns != c->stream) {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);   // tape uploads and scratch reuse are ordered on the context's stream
+    }
+    c->stream = ns;
     return FC_OK;
 }
 
@@ -517,18 +536,47 @@ int32_t fc_tape_create(fc_ctx* c, const uint32_t* words, size_t n_words, uint8_t
     CU(cudaSetDevice(c->device));
     fc_tape* t = new fc_tape();
     t->ctx = c;
-    t->host = cl;
-    t->info.n_ops = uint32_t(cl.size());
-    t->info.ref_len = uint32_t(cl.size());
+    t->host = std::move(cl);
+    t->info.n_ops = uint32_t(t->host.size());
+    t->info.ref_len = uint32_t(t->host.size());
     t->info.choice_count = nch;
     t->info.reg_count = reg_count;
     t->info.mem_count = mem_count;
     t->info.n_vars = n_vars;
     t->info.n_outputs = n_outputs;
     for (int k = 0; k < 3; ++k) t->ax[k] = uint32_t(k) < n_vars ? k : -1;
-    cudaError_t e = cudaMalloc(&t->dev, std::max<size_t>(cl.size(), 1) * sizeof(uint2));
-    if (e == cudaSuccess && !cl.empty())
-        e = cudaMemcpy(t->dev, cl.data(), cl.size() * sizeof(uint2), cudaMemcpyHostToDevice);
+    const size_t need = std::max<size_t>(t->host.size(), 1) * sizeof(uint2);
+    cudaError_t e = cudaSuccess;
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        for (size_t k = 0; k < c->tape_pool.size(); ++k)
+            if (c->tape_pool[k].first >= need && c->tape_pool[k].first <= 2 * need + 4096) {
+                t->dev = c->tape_pool[k].second;
+                t->dev_cap = c->tape_pool[k].first;
+                c->tape_pool.erase(c->tape_pool.begin() + k);
+                break;
+            }
+        if (!t->dev) {
+            e = cudaMalloc(&t->dev, need);
+            t->dev_cap = need;
+        }
+        if (e == cudaSuccess && !t->host.empty()) {
+            if (!c->stage_ev) e = cudaEventCreateWithFlags(&c->stage_ev, cudaEventDisableTiming);
+            else e = cudaEventSynchronize(c->stage_ev);          // the previous upload has left the staging buffer
+            if (e == cudaSuccess && c->stage_cap < need) {
+                if (c->stage) cudaFreeHost(c->stage);
+                c->stage = nullptr;
+                c->stage_cap = 0;
+                e = cudaHostAlloc(&c->stage, need * 2, cudaHostAllocDefault);
+                if (e == cudaSuccess) c->stage_cap = need * 2;
+            }
+            if (e == cudaSuccess) {
+                memcpy(c->stage, t->host.data(), t->host.size() * sizeof(uint2));
+                e = cudaMemcpyAsync(t->dev, c->stage, t->host.size() * sizeof(uint2), cudaMemcpyHostToDevice, c->stream);
+            }
+            if (e == cudaSuccess) e = cudaEventRecord(c->stage_ev, c->stream);
+        }
+    }
     if (e != cudaSuccess) {
         if (t->dev) cudaFree(t->dev);
         delete t;
@@ -547,8 +595,15 @@ int32_t fc_tape_retain(fc_tape* t) {
 int32_t fc_tape_release(fc_tape* t) {
     if (!t) return fail(FC_ERR_INVALID, "null tape");
     if (t->refs.fetch_sub(1) == 1) {
-        cudaSetDevice(t->ctx->device);
-        cudaFree(t->dev);
+        fc_ctx* c = t->ctx;
+        cudaSetDevice(c->device);
+        bool pooled = false;
+        if (t->pooled_ok) {
+            // reuse is ordered on the context's stream, behind whatever still reads this tape
+            std::lock_guard<std::mutex> g(c->mu);
+            if (c->tape_pool.size() < 8) { c->tape_pool.push_back({t->dev_cap, t->dev}); pooled = true; }
+        }
+        if (!pooled) cudaFree(t->dev);
         delete t;
     }
     return FC_OK;
@@ -732,7 +787,8 @@ int32_t fc_simplify(fc_eval* e, const fc_tape* parent, const uint8_t* choices, s
     t->info.ref_len = res[1];
     t->info.choice_count = res[2];
     t->host.resize(res[0]);
-    cudaError_t err = cudaMalloc(&t->dev, std::max<size_t>(res[0], 1) * sizeof(uint2));
+    t->dev_cap = std::max<size_t>(res[0], 1) * sizeof(uint2);
+    cudaError_t err = cudaMalloc(&t->dev, t->dev_cap);
     if (err == cudaSuccess && res[0]) {
         err = cudaMemcpy(t->dev, p.out + (n - res[0]), res[0] * sizeof(uint2), cudaMemcpyDeviceToDevice);
         if (err == cudaSuccess) err = cudaMemcpy(t->host.data(), t->dev, res[0] * sizeof(uint2), cudaMemcpyDeviceToHost);

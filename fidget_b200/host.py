@@ -202,6 +202,14 @@ class TapeData:
         return out
 
     def bytecode(self, repack: bool = True) -> Bytecode:
+        """``fidget_bytecode::Bytecode::new`` for this tape; built once and kept (treat ``words`` as read-only)."""
+        cache = self.__dict__.setdefault("_bytecode", {})
+        if repack in cache:
+            return cache[repack]
+        cache[repack] = self._build_bytecode(repack)
+        return cache[repack]
+
+    def _build_bytecode(self, repack: bool) -> Bytecode:
         n = C.c_size_t()
         rc, mc = C.c_uint8(), C.c_uint32()
         _check(self._lib, self._lib.fh_tape_bytecode(self._h, int(repack), None, 0, C.byref(n),
