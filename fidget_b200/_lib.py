@@ -46,7 +46,7 @@ class FcRender3dCfg(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("depth", C.c_uint32), ("mat", C.c_float * 16),
                 ("n_tile_sizes", C.c_uint32), ("tile_sizes", C.c_uint32 * 8), ("flags", C.c_uint32),
                 ("z_begin", C.c_uint32), ("z_end", C.c_uint32), ("n_var_values", C.c_uint32),
-                ("var_values", C.c_float * 16)]
+                ("var_values", C.c_float * 16), ("root_row_begin", C.c_uint32), ("root_row_end", C.c_uint32)]
 
 
 class FcRenderStats(C.Structure):

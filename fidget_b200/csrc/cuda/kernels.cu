@@ -342,10 +342,10 @@ __global__ void __launch_bounds__(128) k_normals_3d(const __grid_constant__ Norm
     const int lane = threadIdx.x & 31;
     // 8x4 pixel patch per warp
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t patches_x = (p.width + 7u) / 8u, patches_y = (p.height + 3u) / 4u;
+    const uint32_t patches_x = (p.width + 7u) / 8u, patches_y = (p.y1 - p.y0 + 3u) / 4u;
     if (warp >= patches_x * patches_y) return;
-    const uint32_t x = (warp % patches_x) * 8u + (lane & 7), y = (warp / patches_x) * 4u + (lane >> 3);
-    const bool inb = x < p.width && y < p.height;
+    const uint32_t x = (warp % patches_x) * 8u + (lane & 7), y = p.y0 + (warp / patches_x) * 4u + (lane >> 3);
+    const bool inb = x < p.width && y < p.y1;
     const unsigned long long key = inb ? p.heightmap[size_t(y) * p.width + x] : 0ull;
     const uint32_t depth = uint32_t(key >> 32), id = uint32_t(key);
     grd g = gr(0.0f, 0.0f, 0.0f, 0.0f);
@@ -381,7 +381,8 @@ __global__ void __launch_bounds__(128) k_normals_3d(const __grid_constant__ Norm
     }
 }
 void launch_normals_3d(const NormalParams& p, cudaStream_t s) {
-    const uint64_t warps = uint64_t((p.width + 7u) / 8u) * ((p.height + 3u) / 4u);
+    const uint64_t warps = uint64_t((p.width + 7u) / 8u) * ((p.y1 - p.y0 + 3u) / 4u);
+    if (!warps) return;
     k_normals_3d<<<unsigned((warps + 3) / 4), 128, 0, s>>>(p);
 }
 

@@ -174,6 +174,7 @@ struct VoxelParams {
 };
 struct NormalParams {
     uint32_t width, height, depth;
+    uint32_t y0, y1;            // rows to finish (a Y band of a sharded render, else 0..height)
     uint32_t clamp;             // apply the final `depth >= D-1` clamp (voxel.rs:535-546)
     Mat4 mat;
     const TileJob* jobs;        // leaf jobs

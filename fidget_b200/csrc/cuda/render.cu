@@ -249,7 +249,11 @@ int32_t fc_render3d(fc_ctx* c, const fc_tape* tape, const fc_render3d_cfg* cfg, 
     if (rc) return rc;
     const int L = int(ts.size());
     const uint32_t T0 = ts[0];
-    const uint32_t roots_x = (cfg->width + T0 - 1) / T0, roots_y = (cfg->height + T0 - 1) / T0;
+    const uint32_t roots_x = (cfg->width + T0 - 1) / T0, roots_y_all = (cfg->height + T0 - 1) / T0;
+    const uint32_t row0 = cfg->root_row_begin, row1 = cfg->root_row_end ? cfg->root_row_end : roots_y_all;
+    if (row0 > row1 || row1 > roots_y_all) return fail(FC_ERR_INVALID, "bad root row band");
+    const uint32_t roots_y = row1 - row0;
+    const uint32_t band_y0 = std::min(row0 * T0, cfg->height), band_y1 = std::min(row1 * T0, cfg->height);
     const uint32_t z_begin = cfg->z_begin, z_end = cfg->z_end ? cfg->z_end : cfg->depth;
     if (z_begin % T0 || z_begin >= z_end || z_end > ((cfg->depth + T0 - 1) / T0) * T0)
         return fail(FC_ERR_INVALID, "z slab must start on a root-tile boundary inside the volume");
@@ -292,7 +296,7 @@ int32_t fc_render3d(fc_ctx* c, const fc_tape* tape, const fc_render3d_cfg* cfg, 
         }
     }
     CU(cudaMemsetAsync(c->counters.p, 0, sizeof(Counters), s));
-    CU(cudaMemsetAsync(c->heightmap.p, 0, npix * 8, s));
+    CU(cudaMemsetAsync(c->heightmap.as<char>() + size_t(band_y0) * cfg->width * 8, 0, size_t(band_y1 - band_y0) * cfg->width * 8, s));
     if (want_stats) CU(cudaMemsetAsync(c->stats.p, 0, sizeof(Stats), s));
 
     VarBind vb;
@@ -309,7 +313,7 @@ int32_t fc_render3d(fc_ctx* c, const fc_tape* tape, const fc_render3d_cfg* cfg, 
         p.pixel_perfect = 0;
         p.root_mode = (l == 0);
         p.roots_x = roots_x; p.roots_y = roots_y; p.roots_z = roots_z;
-        p.root_x0 = 0; p.root_y0 = 0; p.root_z0 = z_begin;
+        p.root_x0 = 0; p.root_y0 = row0 * T0; p.root_z0 = z_begin;
         p.root_tape.ptr = tape->dev;
         p.root_tape.n_ops = tape->info.n_ops;
         p.root_tape.ref_len = tape->info.ref_len;
@@ -375,6 +379,7 @@ int32_t fc_render3d(fc_ctx* c, const fc_tape* tape, const fc_render3d_cfg* cfg, 
     {
         NormalParams q{};
         q.width = cfg->width; q.height = cfg->height; q.depth = cfg->depth;
+        q.y0 = band_y0; q.y1 = band_y1;
         q.clamp = (cfg->flags & FC_FLAG_NO_CLAMP) ? 0 : 1;
         memcpy(q.mat.m, cfg->mat, sizeof q.mat.m);
         q.jobs = c->jobs[L].as<TileJob>();
@@ -387,7 +392,10 @@ int32_t fc_render3d(fc_ctx* c, const fc_tape* tape, const fc_render3d_cfg* cfg, 
     }
     if (timing) CU(cudaEventRecord(get_event(c, ev++), s));
     CU(cudaGetLastError());
-    if (!out_dev) CU(cudaMemcpyAsync(out, dimg, npix * 16, cudaMemcpyDeviceToHost, s));
+    if (!out_dev && band_y1 > band_y0)
+        CU(cudaMemcpyAsync(reinterpret_cast<char*>(out) + size_t(band_y0) * cfg->width * 16,
+                           static_cast<char*>(dimg) + size_t(band_y0) * cfg->width * 16, size_t(band_y1 - band_y0) * cfg->width * 16,
+                           cudaMemcpyDeviceToHost, s));
     if (async && out_dev && !want_stats) return FC_OK;
     CU(cudaStreamSynchronize(s));
     rc = check_device_errors(c);

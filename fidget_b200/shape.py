@@ -299,6 +299,7 @@ class RenderConfig3D:
     tile_sizes: tuple = ()
     mat: np.ndarray | None = None
     z_range: tuple = (0, 0)
+    root_rows: tuple = (0, 0)                   # band of root-tile rows, full depth (multi-GPU)
     timing: bool = False
     var_values: tuple = ()
     clamp: bool = True                          # False for slab renders (fc_merge_slabs applies it)
@@ -344,6 +345,7 @@ def render3d(shape: CudaShape, cfg: RenderConfig3D, out=None, stats: bool = Fals
     c.flags = (_lib.FC_FLAG_TIMING if cfg.timing else 0) | (_lib.FC_FLAG_ASYNC if asynchronous else 0) | \
         (0 if cfg.clamp else _lib.FC_FLAG_NO_CLAMP)
     c.z_begin, c.z_end = cfg.z_range
+    c.root_row_begin, c.root_row_end = cfg.root_rows
     c.n_var_values = len(cfg.var_values)
     for i, v in enumerate(cfg.var_values):
         c.var_values[i] = float(v)

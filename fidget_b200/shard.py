@@ -1,7 +1,7 @@
 """Multi-GPU partitioning of the renderers (one process per GPU).
 
 The hot path shards without any data-path collective: a rank renders a band of
-root-tile rows (2D) or a Z slab (3D) with the replicated root tape, and ONE
+root-tile rows (2D, or 3D at full depth) or a Z slab (3D) with the replicated root tape, and ONE
 collective (an all-gather of the finished bands / slab images) follows.  The
 reference has no distributed layer; its analogue is rayon over root tiles
 (fidget-raster/src/lib.rs:152-165)."""
@@ -44,6 +44,23 @@ def render2d_bands(shape, cfg, image, gathered, group=None):
     t0 = (cfg.tile_sizes[0] if cfg.tile_sizes else 128)
     rows = band_rows(rank, world, cfg.height, t0)
     render2d(shape, replace(cfg, root_rows=rows), out=image, asynchronous=True)
+    y0, y1 = band_pixels(rows, cfg.width, cfg.height, t0)
+    dist.all_gather_into_tensor(gathered, image[y0:y1], group=group)
+    return gathered
+
+
+def render3d_ybands(shape, cfg, image, gathered, group=None):
+    """One sharded 3D render in Y bands: this rank renders ALL depths of its band of root-tile rows into
+    `image` ([H, W, 4] float32 CUDA tensor viewed as GeometryPixel), then ONE all-gather of the disjoint
+    bands assembles the frame in `gathered` -- no merge pass, 1/world of the slab traffic, and the
+    surface (where the work is) is spread over the ranks instead of sitting in one Z slab."""
+    import torch.distributed as dist
+    from dataclasses import replace
+    from .shape import render3d
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    t0 = (cfg.tile_sizes[0] if cfg.tile_sizes else 128)
+    rows = band_rows(rank, world, cfg.height, t0)
+    render3d(shape, replace(cfg, root_rows=rows), out=image, asynchronous=True)
     y0, y1 = band_pixels(rows, cfg.width, cfg.height, t0)
     dist.all_gather_into_tensor(gathered, image[y0:y1], group=group)
     return gathered

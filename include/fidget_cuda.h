@@ -168,6 +168,10 @@ typedef struct fc_render3d_cfg {
     uint32_t z_begin, z_end;
     uint32_t n_var_values;      /* as in fc_render2d_cfg */
     float var_values[FC_MAX_VARS];
+    /* Y band [row_begin,row_end) of root-tile rows to render, full depth (multi-GPU sharding that
+     * balances surface-like work better than Z slabs); row_end = 0 means all rows.  Only the rows
+     * of the band are written. */
+    uint32_t root_row_begin, root_row_end;
 } fc_render3d_cfg;
 
 typedef struct fc_render_stats {

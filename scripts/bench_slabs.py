@@ -12,6 +12,7 @@ from fidget_b200.shard import render3d_zslabs, z_slab
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+mode = sys.argv[3] if len(sys.argv) > 3 else "zslabs"      # or "ybands"
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -34,14 +35,21 @@ for it in range(2 + steps):
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     e0.record()
     from dataclasses import replace
-    fb.render3d(shape, replace(cfg, z_range=z_slab(rank, world, n, 128), clamp=False), out=slab, asynchronous=True)
-    e1.record()
-    dist.all_gather_into_tensor(gathered, slab)
-    import ctypes as C
-    from fidget_b200 import _lib
-    from fidget_b200.shape import _ck
-    ptrs = (C.c_void_p * world)(*[gathered[r].data_ptr() for r in range(world)])
-    _ck(_lib.load().fc_merge_slabs(cuda._h, ptrs, world, n, n, n, C.c_void_p(out.data_ptr())))
+    if mode == "ybands":
+        from fidget_b200.shard import band_rows
+        rows = band_rows(rank, world, n, 128)
+        fb.render3d(shape, replace(cfg, root_rows=rows), out=slab, asynchronous=True)
+        e1.record()
+        dist.all_gather_into_tensor(out, slab[rows[0] * 128:rows[1] * 128])
+    else:
+        fb.render3d(shape, replace(cfg, z_range=z_slab(rank, world, n, 128), clamp=False), out=slab, asynchronous=True)
+        e1.record()
+        dist.all_gather_into_tensor(gathered, slab)
+        import ctypes as C
+        from fidget_b200 import _lib
+        from fidget_b200.shape import _ck
+        ptrs = (C.c_void_p * world)(*[gathered[r].data_ptr() for r in range(world)])
+        _ck(_lib.load().fc_merge_slabs(cuda._h, ptrs, world, n, n, n, C.c_void_p(out.data_ptr())))
     e2.record()
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e2), e0.elapsed_time(e1)], device=dev)
@@ -51,9 +59,9 @@ for it in range(2 + steps):
 hit = int((out[..., 3].view(torch.int32) > 0).sum())
 if rank == 0:
     ms = sum(times) / len(times)
-    print(json.dumps({"config": f"prospero.vm 3D {n}^3, {world} Z slabs + all-gather + merge", "n_gpus": world, "ms_per_step": ms,
+    print(json.dumps({"config": f"prospero.vm 3D {n}^3, {world} " + ("Y bands (full depth) + all-gather" if mode == "ybands" else "Z slabs + all-gather + merge"), "n_gpus": world, "ms_per_step": ms,
                       "Mvoxels_per_s": n ** 3 / ms / 1e3, "slowest_slab_render_ms": sum(render_ms) / len(render_ms),
-                      "gather_merge_ms": ms - sum(render_ms) / len(render_ms), "gathered_MB_per_rank": world * n * n * 16 / 1e6,
+                      "gather_merge_ms": ms - sum(render_ms) / len(render_ms), "gathered_MB_per_rank": (1 if mode == "ybands" else world) * n * n * 16 / 1e6,
                       "pixels_hit": hit, "steps": steps}), flush=True)
 dist.barrier()
 dist.destroy_process_group()

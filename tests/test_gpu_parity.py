@@ -234,6 +234,19 @@ def _view2(center, scale):
     return np.array([[scale, 0, center[0]], [0, scale, center[1]], [0, 0, 1]], dtype=np.float32)
 
 
+def test_render3d_ybands_assemble_to_full_image(cuda):
+    """3D sharding by bands of root-tile rows (full depth): the bands are disjoint pieces of the full image."""
+    shape = fb.CudaShape.from_vm(cuda, model_text("bear.vm"))
+    n = 512
+    full = fb.render3d(shape, fb.RenderConfig3D(n, n, n))
+    out = np.zeros((n, n), dtype=fb.GEOMETRY_PIXEL)
+    for r in range(4):
+        fb.render3d(shape, fb.RenderConfig3D(n, n, n, root_rows=(r, r + 1)), out=out)
+    assert out.tobytes() == full.tobytes()
+    with pytest.raises(fb.CudaError):
+        fb.render3d(shape, fb.RenderConfig3D(n, n, n, root_rows=(3, 9)))
+
+
 def test_golden_hi_variants(cuda):
     gs = fb.CudaShape.from_vm(cuda, model_text("hi.vm"))
     assert _rows(fb.render2d(gs, fb.RenderConfig2D(32, 32))) == _PIX["check_hi:EXPECTED"]["rows"]
