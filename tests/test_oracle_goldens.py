@@ -13,6 +13,8 @@ from conftest import model_text
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 PIX = json.load(open(os.path.join(GOLD, "pixel_render.json")))
 IVL = json.load(open(os.path.join(GOLD, "interval_known_answers.json")))
+IVL.update(json.load(open(os.path.join(GOLD, "interval_known_answers_manual.json"))))   # transcribed by hand
+POINT = json.load(open(os.path.join(GOLD, "point_known_answers.json")))
 CHOICE = {"Left": 1, "Right": 2, "Both": 3}
 
 
@@ -150,6 +152,45 @@ def test_interval_known_answers(orc, name):
                 assert simplify and choices.tolist() == [CHOICE[c] for c in case["trace"]], (name, case)
 
 
+@pytest.mark.parametrize("name", sorted(POINT))
+def test_point_known_answers(orc, name):
+    """fidget-core/src/eval/test/point.rs: exact values, exact Choice traces, simplified size."""
+    spec = POINT[name]
+    ctx = orc.Context()
+    env = _build(ctx, spec["nodes"])
+    td = ctx.tape(env[spec["root"]])
+    t = orc.Tape.from_data(td)
+    slots = [s for s in td.var_slots()[:2]]
+
+    def run(tape, ins):
+        vars_ = np.zeros(max(td.n_vars, 1), dtype=np.float32)
+        if td.n_vars == 1 and ins:
+            vars_[0] = _f(ins[0])
+        else:
+            for slot, v in zip(slots, ins):
+                if slot >= 0:
+                    vars_[slot] = _f(v)
+        return tape.point_eval(vars_)
+
+    for case in spec["cases"]:
+        out, choices, simplify = run(t, case["inputs"])
+        exp = _f(case["expect"])
+        if isinstance(exp, float) and math.isnan(exp):
+            assert np.isnan(out), (name, case)
+        else:
+            assert out == np.float32(exp), (name, case, out)
+        if "trace" in case:
+            if case["trace"] is None:
+                assert not simplify, (name, case)
+            else:
+                assert simplify and choices.tolist() == [CHOICE[c] for c in case["trace"]], (name, case)
+        if "child_size" in case:
+            child = t.simplify(choices)
+            assert child.size == case["child_size"], (name, child.size)
+            for cc in case["child_cases"]:
+                assert run(child, cc["inputs"])[0] == np.float32(cc["expect"])
+
+
 def test_interval_contains_point_samples(orc):
     """Property test in the spirit of interval.rs:1087-1170: for every op, interval results contain
     point samples (or are the NaN interval)."""
@@ -208,6 +249,42 @@ def test_grad_known_answers(orc, name):
         exp = np.array([_f(v) for v in case["expect"]], dtype=np.float32)
         assert np.array_equal(out, exp) or (np.isnan(exp).any() and np.array_equal(np.isnan(out), np.isnan(exp))), \
             (name, case, out)
+
+
+def test_float_slice_vectorized(orc):
+    """fidget-core/src/eval/test/float_slice.rs:46-90 (test_vectorized): ragged slice lengths."""
+    ctx = orc.Context()
+    x, y = ctx.x(), ctx.y()
+    t = orc.Tape.from_data(ctx.tape(x))
+    for n in (4, 8, 9):
+        v = np.arange(n, dtype=np.float32)
+        assert t.float_slice_eval([v]).tolist() == v.tolist()
+    t = orc.Tape.from_data(ctx.tape(ctx.mul(y, 2.0)))
+    for ins, exp in (([3.0, 2.0, 1.0, 0.0], [6.0, 4.0, 2.0, 0.0]), ([1.0, 4.0, 8.0], [2.0, 8.0, 16.0]),
+                     ([1.0, 4.0, 4.0, -1.0, -2.0, -3.0, 0.0], [2.0, 8.0, 8.0, -2.0, -4.0, -6.0, 0.0])):
+        assert t.float_slice_eval([np.array(ins, dtype=np.float32)]).tolist() == exp
+
+
+def test_grad_add_and_modulo(orc):
+    """grad_slice.rs test_g_add (two-element slices) and test_g_modulo (y - x mod 1)."""
+    ctx = orc.Context()
+    x, y = ctx.x(), ctx.y()
+    td = ctx.tape(ctx.add(x, y))
+    t = orc.Tape.from_data(td)
+    vx, vy, _ = td.var_slots()
+    vars_ = [np.zeros((2, 4), dtype=np.float32) for _ in range(2)]
+    vars_[vx][:, 0] = [0.0, 1.0]          # Grad::from(f32): value only, zero derivative
+    vars_[vy][:, 0] = [2.0, 3.0]
+    assert t.grad_slice_eval(vars_).tolist() == [[2.0, 0.0, 0.0, 0.0], [4.0, 0.0, 0.0, 0.0]]
+
+    td = ctx.tape(ctx.sub(y, ctx.modulo(x, 1.0)))
+    t = orc.Tape.from_data(td)
+    vx, vy, _ = td.var_slots()
+    for xv, exp in ((0.0, [0.5, -1.0, 1.0, 0.0]), (-0.01, [-0.49, -1.0, 1.0, 0.0]), (0.01, [0.49, -1.0, 1.0, 0.0])):
+        vars_ = [np.zeros((1, 4), dtype=np.float32) for _ in range(2)]
+        vars_[vx][0, 0], vars_[vx][0, 1] = xv, 1.0
+        vars_[vy][0, 0], vars_[vy][0, 2] = 0.5, 1.0
+        assert t.grad_slice_eval(vars_)[0].tolist() == [float(np.float32(v)) for v in exp], xv
 
 
 def _test_args():
