@@ -64,6 +64,36 @@ def test_circle_with_bound_var(orc, n_regs):
         assert ascii_rows(orc, img) == PIX[key]["rows"]
 
 
+@pytest.mark.parametrize("n_regs", [255, 3])
+def test_voxel_sphere_with_bound_var(orc, n_regs):
+    """fidget/tests/voxel_render.rs:13-75 (sphere_var + check_sphere): a sphere of variable radius rendered
+    at 32^3 through View3 cameras of scale 1 and 0.5 lands within two voxels of the analytic surface."""
+    ctx = orc.Context()
+    x, y, z = ctx.x(), ctx.y(), ctx.z()
+    r = ctx.sqrt(ctx.add(ctx.add(ctx.square(x), ctx.square(y)), ctx.square(z)))
+    c, _ = ctx.var()
+    td = ctx.tape(ctx.sub(r, c), n_regs)
+    t = orc.Tape.from_data(td)
+    slot = [i for i, (k, _) in enumerate(td.vars()) if k == "v"][0]
+    size = 32
+    m = orc.screen_to_world_3d(size, size, size).astype(np.float64)
+    for scale in (1.0, 0.5):
+        wm = np.diag([scale, scale, scale, 1.0]).astype(np.float32)      # View3::from_center_and_scale(0, scale)
+        for radius in (0.5, 0.75):
+            vv = np.zeros(td.n_vars, dtype=np.float32)
+            vv[slot] = radius
+            img, _ = orc.render3d(t, size, size, size, mat=orc.voxel_mat(size, size, size, wm), var_values=vv)
+            eps = 2.0 / size / scale * 2.0
+            depth = img["depth"].astype(np.int64)
+            ys, xs = np.mgrid[0:size, 0:size]
+            pts = np.stack([xs, ys, depth, np.ones_like(xs)], axis=-1).astype(np.float64) @ m.T
+            pos = pts[..., :3] / pts[..., 3:4] * scale
+            empty, hit = depth == 0, (depth != 0) & (depth != size)       # saturated voxels are skipped
+            assert hit.sum() > 20
+            assert (np.hypot(pos[..., 0], pos[..., 1])[empty] + eps > radius).all()
+            assert (np.abs(radius - np.linalg.norm(pos, axis=-1))[hit] < eps).all()
+
+
 def test_neg_infinity_pixel_perfect(orc):
     # pixel_render.rs:366-377
     ctx = orc.Context()
