@@ -42,6 +42,11 @@ class FcRender2dCfg(C.Structure):
                 ("n_var_values", C.c_uint32), ("var_values", C.c_float * 16)]
 
 
+class FcScheduleInfo(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("suitable", "n_clauses", "n_waves", "widest_wave", "n_tail", "n_segments",
+                                          "n_chain_clauses", "n_slots")]
+
+
 class FcRender3dCfg(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("depth", C.c_uint32), ("mat", C.c_float * 16),
                 ("n_tile_sizes", C.c_uint32), ("tile_sizes", C.c_uint32 * 8), ("flags", C.c_uint32),
@@ -115,6 +120,7 @@ CUDA_API = {
     "fc_render3d": (_i32, [_vp, _vp, _P(FcRender3dCfg), _vp, _P(FcRenderStats)]),
     "fc_merge_slabs": (_i32, [_vp, _P(_vp), _u32, _u32, _u32, _u32, _vp]),
     "fc_octree_sample": (_i32, [_vp, _vp, _P(FcOctreeCfg), _vp, _u64, _P(_u64), _P(FcOctreeStats)]),
+    "fc_schedule_check": (_i32, [_P(_u32), C.c_size_t, _u8, _u32, _u32, _u32, _P(FcScheduleInfo)]),
     "fc_denoise_normals": (_i32, [_vp, _vp, _u32, _u32, _vp]),
     "fc_compute_ssao": (_i32, [_vp, _vp, _u32, _u32, _u32, _vp, _u32, _vp, _u32, _vp]),
     "fc_blur_ssao": (_i32, [_vp, _vp, _u32, _u32, _vp]),

@@ -7,7 +7,7 @@ thread_local std::string g_err;
 
 ////////////////////////////////////////////////////////////////////////////
 // bytecode <-> device clauses
-static int32_t transcode(const uint32_t* words, size_t n_words, uint8_t reg_count, uint32_t mem_count,
+int32_t transcode(const uint32_t* words, size_t n_words, uint8_t reg_count, uint32_t mem_count,
                          uint32_t n_vars, uint32_t n_outputs, std::vector<uint2>& out, uint32_t& n_choices) {
     if (!words || n_words < 4 || (n_words & 1)) return fail(FC_ERR_INVALID, "bytecode: bad length");
     if (words[0] != 0xFFFFFFFFu || words[1] != 0u) return fail(FC_ERR_INVALID, "bytecode: missing start marker");

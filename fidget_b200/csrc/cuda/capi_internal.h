@@ -145,6 +145,8 @@ void upload_schedule(fc_tape* t);
 int coop_blocks(fc_ctx* c, const fc_tape* tape, uint64_t n_roots, LevelParams& p, int dim, int& threads);
 // capi.cu
 int32_t check_device_errors(fc_ctx* c);
+int32_t transcode(const uint32_t* words, size_t n_words, uint8_t reg_count, uint32_t mem_count, uint32_t n_vars,
+                  uint32_t n_outputs, std::vector<uint2>& out, uint32_t& n_choices);
 // render.cu
 int32_t pick_tile_sizes(const uint32_t* ts_in, uint32_t n_in, const uint32_t* dflt, uint32_t n_dflt, uint32_t max_size,
                         std::vector<uint32_t>& ts);

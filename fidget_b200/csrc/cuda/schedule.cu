@@ -182,6 +182,108 @@ static uint64_t fnv1a(const uint2* cl, size_t n) {
     return h;
 }
 
+// Symbolic replay of a coloured schedule (fc_schedule_check): slots hold value ids.
+static int32_t replay_schedule(const std::vector<CoopRec>& recs, const std::vector<CoopFwd>& fwd,
+                               const std::vector<uint32_t>& wave_start, uint32_t tail_begin,
+                               const std::vector<CoopSeg>& segs, uint32_t n_slots) {
+    const uint32_t UNSET = 0xffffffffu;
+    std::vector<uint32_t> holds(n_slots, UNSET);
+    auto bad = [&](size_t i, const char* what) {
+        return fail(FC_ERR_INVALID, std::string("schedule check: record ") + std::to_string(i) + " (clause " +
+                                        std::to_string(recs[i].p) + "): " + what);
+    };
+    // reads of record i against the current slot contents; `skip_prev`: chain records do not load the previous chain value
+    auto check_reads = [&](size_t i, bool chain) -> int32_t {
+        const uint16_t def[2] = {recs[i].ia, recs[i].ib}, sl[2] = {fwd[i].sa, fwd[i].sb};
+        for (int k = 0; k < 2; ++k) {
+            if (def[k] == COOP_NONE) { if (sl[k] != COOP_NONE) return bad(i, "slot for an immediate operand"); continue; }
+            if (chain && sl[k] == COOP_NONE) continue;                 // the previous chain value, carried by the scan
+            if (sl[k] == COOP_NONE || sl[k] >= n_slots) return bad(i, "operand without a slot");
+            if (holds[sl[k]] != def[k]) return bad(i, "operand slot does not hold the defining clause's value");
+        }
+        return FC_OK;
+    };
+    auto step = [&](uint32_t b, uint32_t e, bool chain) -> int32_t {   // records [b, e) run concurrently
+        std::vector<uint8_t> read(n_slots, 0);
+        for (uint32_t i = b; i < e; ++i) {
+            if (int32_t rc = check_reads(i, chain)) return rc;
+            if (fwd[i].sa != COOP_NONE) read[fwd[i].sa] = 1;
+            if (fwd[i].sb != COOP_NONE) read[fwd[i].sb] = 1;
+        }
+        std::vector<uint8_t> written(n_slots, 0);
+        for (uint32_t i = b; i < e; ++i) {
+            const uint16_t so = fwd[i].so;
+            if (so == COOP_NONE) continue;
+            if (so >= n_slots) return bad(i, "result slot out of range");
+            if (read[so] && e - b > 1) return bad(i, "writes a slot that the same step reads");
+            if (written[so]) return bad(i, "two results of one step share a slot");
+            written[so] = 1;
+        }
+        for (uint32_t i = b; i < e; ++i)
+            if (fwd[i].so != COOP_NONE) holds[fwd[i].so] = recs[i].p;
+        return FC_OK;
+    };
+    for (size_t w = 0; w + 1 < wave_start.size(); ++w)
+        if (int32_t rc = step(wave_start[w], wave_start[w + 1], false)) return rc;
+    if (!wave_start.empty() && wave_start.back() != tail_begin) return fail(FC_ERR_INVALID, "schedule check: waves do not end at the tail");
+    uint32_t expect = tail_begin;
+    for (const CoopSeg& sg : segs) {
+        if (sg.begin != expect || sg.end <= sg.begin) return fail(FC_ERR_INVALID, "schedule check: tail segments are not contiguous");
+        expect = sg.end;
+        if (!sg.chain) {
+            for (uint32_t i = sg.begin; i < sg.end; ++i)
+                if (int32_t rc = step(i, i + 1, false)) return rc;
+            continue;
+        }
+        if (sg.begin == 0 || sg.start_slot >= n_slots || holds[sg.start_slot] != recs[sg.begin - 1].p)
+            return bad(sg.begin, "chain does not start from the previous record's value");
+        for (uint32_t i = sg.begin; i < sg.end; ++i) {
+            const uint16_t prev = recs[i - 1].p;
+            const bool a_prev = recs[i].ia == prev, b_prev = recs[i].ib == prev;
+            if (a_prev == b_prev) return bad(i, "chain clause does not combine the previous result with one side");
+            if ((fwd[i].sa == COOP_NONE) != a_prev || (fwd[i].sb == COOP_NONE) != b_prev) return bad(i, "chain operand marking");
+            const uint32_t dop = recs[i].x & 0xff, dop0 = recs[sg.begin].x & 0xff;
+            if (dop != dop0) return bad(i, "mixed opcodes in a chain");
+        }
+        if (int32_t rc = step(sg.begin, sg.end, true)) return rc;
+    }
+    if (expect != recs.size()) return fail(FC_ERR_INVALID, "schedule check: tail segments do not cover the tail");
+    return FC_OK;
+}
+
+extern "C" int32_t fc_schedule_check(const uint32_t* words, size_t n_words, uint8_t reg_count, uint32_t mem_count,
+                                     uint32_t n_vars, uint32_t n_outputs, fc_schedule_info* info) {
+    if (!info) return fail(FC_ERR_INVALID, "null argument");
+    memset(info, 0, sizeof *info);
+    std::vector<uint2> cl;
+    uint32_t nch = 0;
+    if (int32_t rc = transcode(words, n_words, reg_count, mem_count, n_vars, n_outputs, cl, nch)) return rc;
+    info->n_clauses = uint32_t(cl.size());
+    std::vector<CoopRec> recs;
+    std::vector<uint32_t> ws;
+    std::vector<CoopSeg> segs;
+    uint32_t tb = 0;
+    if (cl.size() < 64 || !build_schedule(cl, recs, ws, tb, segs)) return FC_OK;   // not suitable: per-lane kernel
+    std::vector<CoopFwd> fwd;
+    const uint32_t n_slots = colour_slots(recs, ws, segs, fwd);
+    if (!n_slots) return FC_OK;
+    info->suitable = 1;
+    info->n_waves = uint32_t(ws.size() - 1);
+    for (size_t w = 0; w + 1 < ws.size(); ++w) info->widest_wave = std::max(info->widest_wave, ws[w + 1] - ws[w]);
+    info->n_tail = uint32_t(recs.size()) - tb;
+    info->n_segments = uint32_t(segs.size());
+    for (const CoopSeg& sg : segs) if (sg.chain) info->n_chain_clauses += sg.end - sg.begin;
+    info->n_slots = n_slots;
+    // every clause exactly once
+    std::vector<uint8_t> seen(cl.size(), 0);
+    for (const CoopRec& r : recs) {
+        if (r.p >= cl.size() || seen[r.p]) return fail(FC_ERR_INVALID, "schedule check: a clause is missing or scheduled twice");
+        seen[r.p] = 1;
+    }
+    if (recs.size() != cl.size()) return fail(FC_ERR_INVALID, "schedule check: a clause is missing or scheduled twice");
+    return replay_schedule(recs, fwd, ws, tb, segs, n_slots);
+}
+
 void upload_schedule(fc_tape* t) {
     fc_ctx* c = t->ctx;
     if (t->host.size() < 64) return;   // the cooperative kernel is never used for short tapes

@@ -43,6 +43,17 @@ def _ptr(a):
     return C.c_void_p(a.ctypes.data)
 
 
+def schedule_check(tape: TapeData) -> dict:
+    """Host-only: build and symbolically replay the level-0 schedule (waves, chain runs, slot colouring) of
+    ``tape``; raises CudaError if the schedule is inconsistent.  Needs no GPU."""
+    lib = _lib.load()
+    bc = tape.bytecode()
+    info = _lib.FcScheduleInfo()
+    _ck(lib.fc_schedule_check(bc.words.ctypes.data_as(C.POINTER(C.c_uint32)), len(bc.words), bc.reg_count, bc.mem_count,
+                              tape.n_vars, tape.output_count, C.byref(info)))
+    return {n: getattr(info, n) for n, _ in info._fields_}
+
+
 class CudaContext:
     """One GPU: stream + scratch arenas (``fc_ctx``)."""
 

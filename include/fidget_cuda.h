@@ -237,6 +237,19 @@ typedef struct fc_octree_stats {
 int32_t fc_octree_sample(fc_ctx* ctx, const fc_tape* tape, const fc_octree_cfg* cfg, fc_octree_leaf* out,
                          uint64_t cap, uint64_t* n_leaves, fc_octree_stats* stats /* may be NULL */);
 
+/* ---- diagnostics ---------------------------------------------------------- */
+/* Host-only (no device needed): builds the level-0 schedule fc_tape_create would build for this
+ * bytecode -- dependency waves, serial / chain tail segments, slot colouring -- and replays it
+ * symbolically: every operand slot must hold the value of the clause that defines the operand at the
+ * moment it is read, and no clause of a wave (or chain run) may overwrite a slot another clause of
+ * the same step reads.  FC_ERR_INVALID with a message if the check fails; suitable == 0 when the
+ * tape takes the per-lane kernel instead (too short, uses memory slots, ...). */
+typedef struct fc_schedule_info {
+    uint32_t suitable, n_clauses, n_waves, widest_wave, n_tail, n_segments, n_chain_clauses, n_slots;
+} fc_schedule_info;
+int32_t fc_schedule_check(const uint32_t* words, size_t n_words, uint8_t reg_count, uint32_t mem_count,
+                          uint32_t n_vars, uint32_t n_outputs, fc_schedule_info* info);
+
 /* ---- post-processing effects (fidget-raster/src/effects.rs) ---------------- */
 /* Every image pointer may be a host or a device pointer (host images are staged
  * through HBM); images are row-major width*height.  All results are bit-identical
