@@ -311,7 +311,7 @@ def main():
             "gpu_launches": int(stats["kernel_launches"]) * args.steps * frames_per_step,
             "roofline": roofline,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # the CPU baseline is an N = 1 measurement
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line))
     if world > 1:
