@@ -61,3 +61,23 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"(?m)^\s*(from|import)\s+oracle|#include\s+[\"<].*oracle", text):
                     bad.append(f)
     assert not bad, bad
+
+
+def test_header_is_plain_c_and_layouts_agree(tmp_path):
+    """include/fidget_cuda.h must be consumable by a C compiler (it is what cgo / bindgen / JNI read), and the
+    struct sizes the C compiler sees must be the ones the ctypes mirror declares."""
+    import subprocess
+    from fidget_b200 import _lib
+    src = tmp_path / "hdr.c"
+    src.write_text('#include <stdio.h>\n#include "fidget_cuda.h"\nint main(void) {\n'
+                   '  printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(fc_tape_info), sizeof(fc_render2d_cfg), sizeof(fc_render3d_cfg),\n'
+                   '         sizeof(fc_render_stats), sizeof(fc_octree_leaf), sizeof(fc_octree_cfg), sizeof(fc_schedule_info));\n'
+                   '  return 0;\n}\n')
+    exe = tmp_path / "hdr"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           "-o", str(exe), str(src)])
+    sizes = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    mirror = [C.sizeof(t) for t in (_lib.FcTapeInfo, _lib.FcRender2dCfg, _lib.FcRender3dCfg, _lib.FcRenderStats,
+                                    None, _lib.FcOctreeCfg, _lib.FcScheduleInfo) if t is not None]
+    assert sizes[:4] == mirror[:4] and sizes[5:] == mirror[4:]
+    assert sizes[4] == 348
