@@ -81,3 +81,18 @@ def test_header_is_plain_c_and_layouts_agree(tmp_path):
                                     None, _lib.FcOctreeCfg, _lib.FcScheduleInfo) if t is not None]
     assert sizes[:4] == mirror[:4] and sizes[5:] == mirror[4:]
     assert sizes[4] == 348
+
+
+def build_c_example(tmp_path):
+    import subprocess
+    exe = tmp_path / "render2d"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           "-I", os.path.join(ROOT, "fidget_b200", "csrc", "host"), os.path.join(ROOT, "examples", "render2d.c"),
+                           "-L", os.path.join(ROOT, "fidget_b200"), "-lfidget_cuda",
+                           "-Wl,-rpath," + os.path.join(ROOT, "fidget_b200"), "-o", str(exe)])
+    return exe
+
+
+def test_c_client_links_against_the_abi(tmp_path):
+    """examples/render2d.c uses nothing but the two C headers; it must compile as C99 and link."""
+    assert build_c_example(tmp_path).exists()

@@ -1,10 +1,12 @@
 """GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle
 on identical tapes and inputs."""
+import os
+
 import numpy as np
 import pytest
 
 import fidget_b200 as fb
-from conftest import model_text, same_f32
+from conftest import MODELS as MODELS_DIR, model_text, same_f32
 
 pytestmark = pytest.mark.gpu
 
@@ -506,3 +508,19 @@ def test_constant_and_single_axis_shapes(orc, cuda):
         o3, _ = orc.render3d(ot, 64, 64, 64)
         g3 = fb.render3d(gs, fb.RenderConfig3D(64, 64, 64))
         _cmp3d(g3, o3, exact_normals=True)
+
+
+def test_c_client_renders_like_the_python_face(cuda, tmp_path):
+    """examples/render2d.c (plain C over the C ABI: fh_* front end + fc_tape_create + fc_render2d) produces the
+    same RawDistancePixel words as fidget_b200.render2d."""
+    import subprocess
+    from test_capi_symbols import build_c_example
+    exe = build_c_example(tmp_path)
+    for name, size in (("hi.vm", 64), ("prospero.vm", 512)):
+        out = subprocess.check_output([str(exe), os.path.join(MODELS_DIR, name), str(size)], text=True)
+        img = fb.render2d(fb.CudaShape.from_vm(cuda, model_text(name)), fb.RenderConfig2D(size, size))
+        h = 1469598103934665603
+        for b in img.view(np.uint32).ravel().tolist():
+            h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        assert f"inside {int(fb.pixel_inside(img).sum())} px" in out, out
+        assert f"fnv1a {h:016x}" in out, out
