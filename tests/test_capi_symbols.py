@@ -96,3 +96,13 @@ def build_c_example(tmp_path):
 def test_c_client_links_against_the_abi(tmp_path):
     """examples/render2d.c uses nothing but the two C headers; it must compile as C99 and link."""
     assert build_c_example(tmp_path).exists()
+
+
+def test_generated_rust_binding_is_current():
+    """bindings/rust/ffi.rs is generated from the header; it must not be stale and must declare every fc_* symbol."""
+    import subprocess
+    import sys
+    assert subprocess.call([sys.executable, os.path.join(ROOT, "scripts", "gen_rust_ffi.py"), "--check"]) == 0
+    rs = open(os.path.join(ROOT, "bindings", "rust", "ffi.rs")).read()
+    for name in declared("include/fidget_cuda.h", "fc_"):
+        assert f"pub fn {name}(" in rs, name
