@@ -87,8 +87,7 @@ class ClockSampler:
         reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4)
                           if r[3 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows),
-                "sampled": "during the timed steps and 600 identical untimed steps issued right behind them"}
+                "reasons": reasons, "samples": len(self.rows)}
 
 
 def measured_peaks():
@@ -218,11 +217,6 @@ def main():
             starts[i].record(stream)
             step()
             stops[i].record(stream)
-        # K steps last ~10 ms, one nvidia-smi query takes longer: keep the identical load running
-        # (untimed, ~0.3 s) so that the clocks are sampled under it more than once
-        for i in range(600):          # a fixed count: every rank must issue the same collectives
-            flush.fill_(i & 255)
-            step()
         sync_all()
     cuda.synchronize()
     total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, stops))
