@@ -54,6 +54,32 @@ class ClockSampler:
         self.stop = False
         self.index = index
         self.t = None
+        # NVML answers in ~0.1 ms, nvidia-smi (the same counters through a subprocess) in ~50 ms; the
+        # timed region of a default run lasts ~10 ms, so NVML is what can sample it more than once
+        self.nvml, self.handle = None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        p, h = self.nvml, self.handle
+        sm = p.nvmlDeviceGetClockInfo(h, p.NVML_CLOCK_SM)
+        mx = p.nvmlDeviceGetMaxClockInfo(h, p.NVML_CLOCK_SM)
+        try:
+            r = p.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            r = p.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        try:
+            w = p.nvmlDeviceGetPowerUsage(h) / 1000.0
+        except Exception:
+            w = 0.0
+        bits = (p.nvmlClocksThrottleReasonHwSlowdown, p.nvmlClocksThrottleReasonHwThermalSlowdown,
+                p.nvmlClocksThrottleReasonSwThermalSlowdown, p.nvmlClocksThrottleReasonSwPowerCap)
+        self.rows.append([str(sm), str(mx), f"{w:.1f}"] + ["Active" if r & b else "Not Active" for b in bits])
 
     def _sample(self):
         try:
@@ -66,6 +92,13 @@ class ClockSampler:
 
     def _run(self):
         while not self.stop:
+            if self.nvml is not None:
+                try:
+                    self._sample_nvml()
+                    time.sleep(0.001)
+                    continue
+                except Exception:
+                    self.nvml = None          # fall back to nvidia-smi for the rest of the run
             self._sample()
             time.sleep(0.05)
 
@@ -87,7 +120,8 @@ class ClockSampler:
         reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4)
                           if r[3 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(self.rows),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def measured_peaks():
