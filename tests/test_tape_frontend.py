@@ -36,6 +36,25 @@ def test_ssa_dupe_and_constant(Ctx):
     assert t.info.ssa_len == 2 and t.n_vars == 0      # CopyImm, output
 
 
+def test_context_ring_and_dupe_vmdata_len(Ctx):
+    # fidget-core/src/context/mod.rs:1609-1637 (VmData::len counts register-tape clauses)
+    ctx = Ctx()
+    c0 = ctx.constant(0.5)
+    x, y = ctx.x(), ctx.y()
+    r = ctx.add(ctx.square(x), ctx.square(y))
+    c9 = ctx.max(ctx.sub(ctx.constant(0.25), r), ctx.sub(r, c0))
+    t = ctx.tape(c9)
+    assert len(t) == 9 and t.n_vars == 2
+    ctx = Ctx()
+    x = ctx.x()
+    t = ctx.tape(ctx.mul(x, x))
+    assert len(t) == 3 and t.n_vars == 1
+    # import_optimization (mod.rs:1665-1671): x + 0 folds to x
+    ctx = Ctx()
+    x = ctx.x()
+    assert ctx.add(x, 0.0) == x
+
+
 def test_vmdata_doc_example(Ctx):
     # fidget-core/src/vm/data.rs:46-58
     ctx = Ctx()
