@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import model_text
+from conftest import model_text, same_f32
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 PIX = json.load(open(os.path.join(GOLD, "pixel_render.json")))
@@ -463,3 +463,35 @@ def test_octree_cube_single_edge(orc):
     present = ((leaves["present"][:, None] >> np.arange(12)[None, :]) & 1).astype(bool)
     g = leaves["grad"][present][:, :3]
     assert np.all((np.abs(g) == 1).sum(axis=1) == 1)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_simplified_tapes_agree_with_their_parent_inside_the_box(orc, seed):
+    """The contract of VmData::simplify (vm/data.rs:123-318) that every renderer relies on: a tape simplified
+    with the trace of an interval evaluation computes the same values as its parent everywhere inside that
+    interval -- point results bit for bit, and the interval result over the same box."""
+    from test_gpu_fuzz import random_shape
+    rng = np.random.default_rng(500 + seed)
+    ctx = orc.Context()
+    td = ctx.tape(random_shape(ctx, rng, int(rng.integers(6, 60)), use_z=bool(seed % 2)))
+    parent = orc.Tape.from_data(td)
+    nv = max(td.n_vars, 1)
+    checked = 0
+    for _ in range(40):
+        c = rng.uniform(-1, 1, nv).astype(np.float32)
+        w = (rng.uniform(0, 1, nv) ** 3 * 0.6).astype(np.float32)
+        box = np.stack([c - w, c + w], axis=-1).astype(np.float32)
+        out, choices, simplify = parent.interval_eval(box)
+        if not simplify:
+            continue
+        child = parent.simplify(choices)
+        assert child.size <= parent.size
+        o2, _, _ = child.interval_eval(box)
+        assert same_f32(o2, out)
+        for _ in range(16):
+            pt = (box[:, 0] + (box[:, 1] - box[:, 0]) * rng.random(nv).astype(np.float32)).astype(np.float32)
+            pt = np.minimum(np.maximum(pt, box[:, 0]), box[:, 1])
+            a, b = parent.point_eval(pt)[0], child.point_eval(pt)[0]
+            assert same_f32(a, b), (seed, pt, a, b)
+        checked += 1
+    assert checked > 0
