@@ -1,0 +1,99 @@
+"""The oracle's tile renderers against brute force: every pixel / voxel evaluated one by one with the
+(separately pinned) float and gradient evaluators.  This is what the tile recursion, the interval
+proofs and the chain of tape simplifications must reproduce exactly (pixel.rs:316-440, voxel.rs:244-553)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import model_text, same_f32
+from test_gpu_fuzz import random_shape
+
+
+def model_points(orc, mat, xs, ys, zs):
+    """transform_f32 of the oracle for every (x, y, z): the model-space point a pixel / voxel is evaluated at."""
+    m = np.ascontiguousarray(mat, dtype=np.float32).reshape(16)
+    fp = C.POINTER(C.c_float)
+    out = np.zeros((len(xs), 3), dtype=np.float32)
+    tmp = np.zeros(3, dtype=np.float32)
+    f = orc.lib().orc_transform_f32
+    for i, (x, y, z) in enumerate(zip(xs, ys, zs)):
+        f(m.ctypes.data_as(fp), float(x), float(y), float(z), tmp.ctypes.data_as(fp))
+        out[i] = tmp
+    return out
+
+
+def axis_columns(t, pts):
+    """SoA inputs in the tape's own input-slot order (ShapeTape::vars, shape/mod.rs:355-376)."""
+    slots = t.data.var_slots()
+    cols = [np.zeros(len(pts), dtype=np.float32) for _ in range(max(t.n_vars, 1))]
+    for axis, slot in enumerate(slots):
+        if slot >= 0:
+            cols[slot] = np.ascontiguousarray(pts[:, axis])
+    return cols, slots
+
+
+def tapes(orc):
+    yield "hi.vm", orc.Tape.from_vm(model_text("hi.vm")), None
+    yield "quarter.vm", orc.Tape.from_vm(model_text("quarter.vm")), None
+    yield "prospero.vm", orc.Tape.from_vm(model_text("prospero.vm")), None
+    for seed in range(4):
+        ctx = orc.Context()
+        td = ctx.tape(random_shape(ctx, np.random.default_rng(40 + seed), 20 + 10 * seed, use_z=False))
+        yield f"csg{seed}", orc.Tape.from_data(td), td
+
+
+@pytest.mark.parametrize("size,tile_sizes", [(64, (32, 8)), (96, (32, 16, 8))])
+def test_render2d_equals_brute_force(orc, size, tile_sizes):
+    for name, t, _ in tapes(orc):
+        img, st = orc.render2d(t, size, size, tile_sizes=tile_sizes)
+        ys, xs = np.mgrid[0:size, 0:size]
+        pts = model_points(orc, orc.pixel_mat(size, size), xs.ravel(), ys.ravel(), np.zeros(size * size))
+        brute = t.float_slice_eval(axis_columns(t, pts)[0]).reshape(size, size)
+        bits = img.view(np.uint32)
+        is_fill = np.isnan(img) & ((bits & np.uint32(0xFF << 9)) == np.uint32(0xF6 << 9))
+        # interval-proven tiles: the proof is sound at every pixel; shaded pixels: the simplified leaf tape
+        # returns what the root tape returns
+        assert np.array_equal(orc.pixel_inside(img), brute < 0), name
+        assert same_f32(img[~is_fill], brute[~is_fill]), name
+        assert is_fill.sum() + st["pixels"] == size * size, name
+
+
+@pytest.mark.parametrize("name", ["sphere", "bear.vm", "csg"])
+def test_render3d_equals_brute_force(orc, name):
+    size = 32
+    if name == "sphere":
+        ctx = orc.Context()
+        x, y, z = ctx.x(), ctx.y(), ctx.z()
+        td = ctx.tape(ctx.sub(ctx.sqrt(ctx.add(ctx.add(ctx.square(x), ctx.square(y)), ctx.square(z))), 0.6))
+        t = orc.Tape.from_data(td)
+    elif name == "csg":
+        ctx = orc.Context()
+        td = ctx.tape(random_shape(ctx, np.random.default_rng(7), 12, use_z=True))
+        t = orc.Tape.from_data(td)
+    else:
+        t = orc.Tape.from_vm(model_text(name))
+    img, _ = orc.render3d(t, size, size, size, tile_sizes=(16, 8))
+    zs, ys, xs = np.mgrid[0:size, 0:size, 0:size]
+    pts = model_points(orc, orc.voxel_mat(size, size, size), xs.ravel(), ys.ravel(), zs.ravel())
+    vals = t.float_slice_eval(axis_columns(t, pts)[0]).reshape(size, size, size)
+    inside = vals < 0                                                  # [z, y, x]
+    top = np.where(inside.any(axis=0), size - np.argmax(inside[::-1], axis=0), 0)   # highest inside voxel + 1
+    # voxel.rs:535-546: a column that reaches the top of the volume saturates to depth = size
+    assert np.array_equal(np.minimum(img["depth"], size), np.minimum(top, size)), name
+    # normals: gradient at the surface voxel (voxel.rs:449-481); saturated columns get [0, 0, 1]
+    hit = (img["depth"] > 0) & (img["depth"] < size - 1)
+    yy, xx = np.nonzero(hit)
+    zz = img["depth"][hit].astype(np.int64) - 1
+    p = model_points(orc, orc.voxel_mat(size, size, size), xx, yy, zz)
+    # the renderer differentiates with respect to the VOXEL coordinates: the seeds are the rows of the (affine)
+    # screen-to-model matrix (Transformable for Grad, shape/mod.rs:918-948)
+    M = np.asarray(orc.voxel_mat(size, size, size), dtype=np.float32).reshape(4, 4)
+    slots = t.data.var_slots()
+    vars_ = [np.zeros((len(xx), 4), dtype=np.float32) for _ in range(max(t.n_vars, 1))]
+    for axis, slot in enumerate(slots):
+        if slot >= 0:
+            vars_[slot][:, 0] = p[:, axis]
+            vars_[slot][:, 1:4] = M[axis, :3]
+    grads = t.grad_slice_eval(vars_)
+    assert same_f32(img["normal"][hit], grads[:, 1:4]), name
