@@ -97,3 +97,35 @@ def test_render3d_equals_brute_force(orc, name):
             vars_[slot][:, 1:4] = M[axis, :3]
     grads = t.grad_slice_eval(vars_)
     assert same_f32(img["normal"][hit], grads[:, 1:4]), name
+
+
+@pytest.mark.parametrize("name", ["sphere", "colonnade.vm", "csg"])
+def test_octree_leaves_equal_brute_force_corner_masks(orc, name):
+    """OctreeBuilder::leaf (octree.rs:590-640): a depth-D cell is a surface leaf iff its 8 corner samples differ
+    in sign; bit i of the mask is set when corner i (x = bit 0, y = bit 1, z = bit 2) is inside.  The interval
+    descent may only discard cells whose corners all agree."""
+    depth = 4
+    if name == "sphere":
+        ctx = orc.Context()
+        x, y, z = ctx.x(), ctx.y(), ctx.z()
+        t = orc.Tape.from_data(ctx.tape(ctx.sub(ctx.sqrt(ctx.add(ctx.add(ctx.square(x), ctx.square(y)), ctx.square(z))), 0.6)))
+    elif name == "csg":
+        ctx = orc.Context()
+        t = orc.Tape.from_data(ctx.tape(random_shape(ctx, np.random.default_rng(11), 10, use_z=True)))
+    else:
+        t = orc.Tape.from_vm(model_text(name))
+    leaves, _ = orc.octree_sample(t, depth)
+    n = 1 << depth
+    g = (np.arange(n + 1, dtype=np.float32) * np.float32(2.0 / n) - np.float32(1.0)).astype(np.float32)   # CellBounds: dyadic, exact
+    zz, yy, xx = np.meshgrid(g, g, g, indexing="ij")
+    pts = np.stack([xx.ravel(), yy.ravel(), zz.ravel()], axis=-1)
+    inside = (t.float_slice_eval(axis_columns(t, pts)[0]) < 0).reshape(n + 1, n + 1, n + 1)     # [z, y, x]
+    mask = np.zeros((n, n, n), dtype=np.uint16)
+    for i in range(8):
+        dx, dy, dz = i & 1, (i >> 1) & 1, (i >> 2) & 1
+        mask |= inside[dz:dz + n, dy:dy + n, dx:dx + n].astype(np.uint16) << i
+    surface = (mask != 0) & (mask != 255)
+    want = {(int(x), int(y), int(z)): int(mask[z, y, x]) for z, y, x in zip(*np.nonzero(surface))}
+    got = {(int(l["ix"]), int(l["iy"]), int(l["iz"])): int(l["mask"]) for l in leaves}
+    assert got == want, (name, len(got), len(want))
+    assert len(got) > 50
