@@ -129,3 +129,45 @@ def test_octree_leaves_equal_brute_force_corner_masks(orc, name):
     got = {(int(l["ix"]), int(l["iy"]), int(l["iz"])): int(l["mask"]) for l in leaves}
     assert got == want, (name, len(got), len(want))
     assert len(got) > 50
+
+
+def test_octree_edge_intersections_bracket_the_surface(orc):
+    """OctreeBuilder::leaf edge search (octree.rs:642-740): four rounds of 16-ary search leave a bracket of
+    1/65536 of the edge, the intersection is its midpoint: it lies ON the cell edge, and the field changes sign
+    (or vanishes) within half a bracket either side of it."""
+    depth = 3
+    ctx = orc.Context()
+    x, y, z = ctx.x(), ctx.y(), ctx.z()
+    r = ctx.sqrt(ctx.add(ctx.add(ctx.square(x), ctx.square(y)), ctx.square(z)))
+    t = orc.Tape.from_data(ctx.tape(ctx.sub(r, 0.6)))
+    leaves, _ = orc.octree_sample(t, depth)
+    h = 2.0 / (1 << depth)
+    lo_pts, hi_pts, n_edges = [], [], 0
+    for l in leaves:
+        origin = np.array([l["ix"], l["iy"], l["iz"]], dtype=np.float64) * h - 1.0
+        for e in range(12):
+            if not (int(l["present"]) >> e) & 1:
+                continue
+            ta, u, v = e >> 2, e & 1, (e >> 1) & 1
+            ua, va = (ta + 1) % 3, (ta + 2) % 3
+            base = origin.copy()
+            base[ua] += u * h
+            base[va] += v * h
+            pos = l["pos"][e].astype(np.float64)
+            assert abs(pos[ua] - base[ua]) < 1e-6 and abs(pos[va] - base[va]) < 1e-6, (e, pos, base)
+            assert base[ta] - 1e-6 <= pos[ta] <= base[ta] + h + 1e-6
+            d = np.zeros(3)
+            d[ta] = h / 65536.0
+            lo_pts.append(pos - d)
+            hi_pts.append(pos + d)
+            n_edges += 1
+    assert n_edges > 100
+    a = t.float_slice_eval(axis_columns(t, np.array(lo_pts, dtype=np.float32))[0])
+    b = t.float_slice_eval(axis_columns(t, np.array(hi_pts, dtype=np.float32))[0])
+    assert np.all(a * b <= 0.0)
+    # the Hermite normal of a sphere at the intersection is radial
+    for l in leaves[:50]:
+        for e in range(12):
+            if (int(l["present"]) >> e) & 1:
+                g, p = l["grad"][e][:3].astype(np.float64), l["pos"][e].astype(np.float64)
+                assert np.allclose(g / np.linalg.norm(g), p / np.linalg.norm(p), atol=1e-4)
