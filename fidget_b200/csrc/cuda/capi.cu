@@ -177,7 +177,6 @@ int32_t fc_ctx_set_arena_bytes(fc_ctx* c, uint64_t bytes) {
 int32_t fc_tape_create(fc_ctx* c, const uint32_t* words, size_t n_words, uint8_t reg_count, uint32_t mem_count,
                        uint32_t n_vars, uint32_t n_outputs, uint32_t choice_count, fc_tape** out) {
     if (!c || !out) return fail(FC_ERR_INVALID, "null argument");
-    if (reg_count == 255) return fail(FC_ERR_INVALID, "register 255 is reserved");
     if (mem_count > 2048 - MEM_BASE) return fail(FC_ERR_UNSUPPORTED, "too many memory slots (max 1792)");
     std::vector<uint2> cl;
     uint32_t nch = 0;

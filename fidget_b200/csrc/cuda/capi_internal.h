@@ -122,7 +122,7 @@ struct fc_tape {
 struct Sched {
     int device = 0;
     uint64_t hash = 0;
-    size_t n_clauses = 0;
+    std::vector<uint2> clauses;
     CoopRec* d_recs = nullptr;
     CoopFwd* d_fwd = nullptr;
     uint32_t* d_wave_start = nullptr;

@@ -453,13 +453,15 @@ __global__ void __launch_bounds__(128) k_pixels_2d(const __grid_constant__ Pixel
 void launch_pixels_2d(const PixelParams& p, int blocks, cudaStream_t s) { k_pixels_2d<<<blocks, 128, 0, s>>>(p); }
 
 // ---------------------------------------------------------------------------
-// Fill painter: one warp per (record, 1024-pixel unit)
+// Fill painter: one warp per (record, unit of <= 1024 pixels).  Any tile edge T works: the last
+// unit of a tile may be partial, and tiles whose edge is not a multiple of four (a 4-pixel group
+// would straddle two rows) take the per-pixel path.
 __global__ void __launch_bounds__(256) k_fill_2d(const __grid_constant__ FillParams p) {
     const uint32_t n = *p.n_fills;
     const uint32_t T = p.tile;
     const uint32_t tile_px = T * T;
     const uint32_t unit_px = min(tile_px, 1024u);
-    const uint32_t units = tile_px / unit_px;
+    const uint32_t units = (tile_px + unit_px - 1u) / unit_px;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -471,15 +473,17 @@ __global__ void __launch_bounds__(256) k_fill_2d(const __grid_constant__ FillPar
         const float v = __uint_as_float(fr.value);
         const uint32_t first = u * unit_px;
         for (uint32_t q = lane * 4u; q < unit_px; q += 128u) {
-            uint32_t pix = first + q;
-            uint32_t x = fr.x + pix % T, y = fr.y + pix / T;
-            if (y >= p.height) continue;
-            float* dst = p.out + size_t(y) * p.width + x;
-            if (vec_ok && x + 3u < p.width) {
-                *reinterpret_cast<float4*>(dst) = make_float4(v, v, v, v);
+            const uint32_t pix = first + q;
+            if (pix >= tile_px) break;
+            if (vec_ok) {   // T % 4 == 0: the group lies in one row, 16-byte aligned
+                const uint32_t x = fr.x + pix % T, y = fr.y + pix / T;
+                if (y >= p.height || x >= p.width) continue;
+                *reinterpret_cast<float4*>(p.out + size_t(y) * p.width + x) = make_float4(v, v, v, v);   // width % 4 == 0
             } else {
-                for (uint32_t k = 0; k < 4u; ++k)
-                    if (x + k < p.width && (pix + k) / T == pix / T) dst[k] = v;
+                for (uint32_t k = 0; k < 4u && pix + k < tile_px; ++k) {
+                    const uint32_t x = fr.x + (pix + k) % T, y = fr.y + (pix + k) / T;
+                    if (x < p.width && y < p.height) p.out[size_t(y) * p.width + x] = v;
+                }
             }
         }
     }

@@ -49,7 +49,7 @@ extern "C" {
 int32_t fc_render2d(fc_ctx* c, const fc_tape* tape, const fc_render2d_cfg* cfg, float* out, fc_render_stats* stats) {
     if (!c || !tape || !cfg || !out) return fail(FC_ERR_INVALID, "null argument");
     if (cfg->width == 0 || cfg->height == 0) return fail(FC_ERR_INVALID, "empty image");
-    if (tape->info.mem_count) return fail(FC_ERR_UNSUPPORTED, "renderers need a tape without memory spills (<= 254 registers)");
+    if (tape->info.mem_count) return fail(FC_ERR_UNSUPPORTED, "renderers need a tape without memory spills (<= 255 registers)");
     if (tape->info.n_outputs != 1) return fail(FC_ERR_INVALID, "ShapeTape has multiple outputs");
     std::lock_guard<std::mutex> guard(c->mu);
     CU(cudaSetDevice(c->device));
@@ -198,7 +198,12 @@ int32_t fc_render2d(fc_ctx* c, const fc_tape* tape, const fc_render2d_cfg* cfg, 
     }
     if (timing) CU(cudaEventRecord(get_event(c, ev++), s));
     CU(cudaGetLastError());
-    if (!out_dev) CU(cudaMemcpyAsync(out, dimg, img_bytes, cudaMemcpyDeviceToHost, s));
+    if (!out_dev) {   // only the rows of the requested band are copied back
+        const uint32_t by0 = std::min(row0 * T0, cfg->height), by1 = std::min(row1 * T0, cfg->height);
+        if (by1 > by0)
+            CU(cudaMemcpyAsync(out + size_t(by0) * cfg->width, dimg + size_t(by0) * cfg->width,
+                               size_t(by1 - by0) * cfg->width * 4, cudaMemcpyDeviceToHost, s));
+    }
     if (async && out_dev && !want_stats) return FC_OK;
     CU(cudaStreamSynchronize(s));
     rc = check_device_errors(c);
@@ -239,7 +244,7 @@ int32_t fc_render3d(fc_ctx* c, const fc_tape* tape, const fc_render3d_cfg* cfg, 
                     fc_render_stats* stats) {
     if (!c || !tape || !cfg || !out) return fail(FC_ERR_INVALID, "null argument");
     if (cfg->width == 0 || cfg->height == 0 || cfg->depth == 0) return fail(FC_ERR_INVALID, "empty volume");
-    if (tape->info.mem_count) return fail(FC_ERR_UNSUPPORTED, "renderers need a tape without memory spills (<= 254 registers)");
+    if (tape->info.mem_count) return fail(FC_ERR_UNSUPPORTED, "renderers need a tape without memory spills (<= 255 registers)");
     if (tape->info.n_outputs != 1) return fail(FC_ERR_INVALID, "ShapeTape has multiple outputs");
     std::lock_guard<std::mutex> guard(c->mu);
     CU(cudaSetDevice(c->device));

@@ -291,7 +291,8 @@ void upload_schedule(fc_tape* t) {
     {
         std::lock_guard<std::mutex> g(c->mu);
         for (auto& sp : c->sched_cache)
-            if (sp && sp->hash == h && sp->n_clauses == t->host.size()) { t->sched = sp; return; }
+            if (sp && sp->hash == h && sp->clauses.size() == t->host.size() &&
+                memcmp(sp->clauses.data(), t->host.data(), t->host.size() * sizeof(uint2)) == 0) { t->sched = sp; return; }
     }
     std::vector<CoopRec> recs;
     std::vector<uint32_t> ws;
@@ -299,7 +300,7 @@ void upload_schedule(fc_tape* t) {
     auto sc = std::make_shared<Sched>();
     sc->device = c->device;
     sc->hash = h;
-    sc->n_clauses = t->host.size();
+    sc->clauses = t->host;   // a hash hit is verified against the clauses themselves
     if (!build_schedule(t->host, recs, ws, tb, sc->segs)) return;
     std::vector<CoopFwd> fwd;
     sc->n_slots = colour_slots(recs, ws, sc->segs, fwd);

@@ -63,6 +63,7 @@ class CudaContext:
         _ck(self._lib.fc_ctx_create(device, C.byref(h)))
         self._h = h
         self.device = device
+        self._stream = None
 
     def close(self):
         if getattr(self, "_h", None):
@@ -78,6 +79,27 @@ class CudaContext:
             _ck(self._lib.fc_ctx_set_stream(self._h, None, 1))
         else:
             _ck(self._lib.fc_ctx_set_stream(self._h, C.c_void_p(cuda_stream), 0))
+        self._stream = cuda_stream
+
+    def on_stream(self, cuda_stream: int):
+        """Context manager: enqueue on ``cuda_stream`` (e.g. ``torch.cuda.current_stream().cuda_stream``) inside
+        the block, then go back to whatever stream was bound before.  A no-op when already bound to it."""
+        ctx = self
+
+        class _Bound:
+            def __enter__(self_b):
+                self_b.prev = getattr(ctx, "_stream", None)
+                self_b.changed = self_b.prev != cuda_stream
+                if self_b.changed:
+                    ctx.set_stream(cuda_stream)
+                return ctx
+
+            def __exit__(self_b, *a):
+                if self_b.changed:
+                    ctx.set_stream(self_b.prev)
+                return False
+
+        return _Bound()
 
     def synchronize(self):
         _ck(self._lib.fc_ctx_synchronize(self._h))

@@ -33,19 +33,28 @@ def z_slab(rank: int, world: int, depth: int, root_tile: int = 128):
     return rank * per * root_tile, (rank + 1) * per * root_tile
 
 
+def _on_torch_stream(shape):
+    """The renderers enqueue on the fc_ctx's stream, the collective on torch's current stream: bind
+    the context to torch's current stream for the duration of the call so that both are ordered
+    (a no-op when the caller has already done so with ``CudaContext.set_stream``)."""
+    import torch
+    return shape.cuda.on_stream(torch.cuda.current_stream().cuda_stream)
+
+
 def render2d_bands(shape, cfg, image, gathered, group=None):
     """One sharded 2D frame: this rank renders its band of root-tile rows into `image`
     (a CUDA tensor [H, W] float32), then ONE all-gather assembles all bands into `gathered`.
-    Enqueues on the current stream; returns `gathered`."""
+    Enqueues on torch's current stream (the context is bound to it for the call); returns `gathered`."""
     import torch.distributed as dist
     from dataclasses import replace
     from .shape import render2d
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     t0 = (cfg.tile_sizes[0] if cfg.tile_sizes else 128)
     rows = band_rows(rank, world, cfg.height, t0)
-    render2d(shape, replace(cfg, root_rows=rows), out=image, asynchronous=True)
     y0, y1 = band_pixels(rows, cfg.width, cfg.height, t0)
-    dist.all_gather_into_tensor(gathered, image[y0:y1], group=group)
+    with _on_torch_stream(shape):
+        render2d(shape, replace(cfg, root_rows=rows), out=image, asynchronous=True)
+        dist.all_gather_into_tensor(gathered, image[y0:y1], group=group)
     return gathered
 
 
@@ -60,9 +69,10 @@ def render3d_ybands(shape, cfg, image, gathered, group=None):
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     t0 = (cfg.tile_sizes[0] if cfg.tile_sizes else 128)
     rows = band_rows(rank, world, cfg.height, t0)
-    render3d(shape, replace(cfg, root_rows=rows), out=image, asynchronous=True)
     y0, y1 = band_pixels(rows, cfg.width, cfg.height, t0)
-    dist.all_gather_into_tensor(gathered, image[y0:y1], group=group)
+    with _on_torch_stream(shape):
+        render3d(shape, replace(cfg, root_rows=rows), out=image, asynchronous=True)
+        dist.all_gather_into_tensor(gathered, image[y0:y1], group=group)
     return gathered
 
 
@@ -78,9 +88,10 @@ def render3d_zslabs(shape, cfg, slab, gathered, out, group=None):
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     t0 = (cfg.tile_sizes[0] if cfg.tile_sizes else 128)
     zr = z_slab(rank, world, cfg.depth, t0)
-    render3d(shape, replace(cfg, z_range=zr, clamp=False), out=slab, asynchronous=True)
-    dist.all_gather_into_tensor(gathered, slab, group=group)
-    ptrs = (C.c_void_p * world)(*[gathered[r].data_ptr() for r in range(world)])
-    _ck(_lib.load().fc_merge_slabs(shape.cuda._h, ptrs, world, cfg.width, cfg.height, cfg.depth,
-                                   C.c_void_p(out.data_ptr())))
+    with _on_torch_stream(shape):
+        render3d(shape, replace(cfg, z_range=zr, clamp=False), out=slab, asynchronous=True)
+        dist.all_gather_into_tensor(gathered, slab, group=group)
+        ptrs = (C.c_void_p * world)(*[gathered[r].data_ptr() for r in range(world)])
+        _ck(_lib.load().fc_merge_slabs(shape.cuda._h, ptrs, world, cfg.width, cfg.height, cfg.depth,
+                                       C.c_void_p(out.data_ptr())))
     return out

@@ -6,6 +6,7 @@
 
 #include "../fidget_b200/csrc/host/host_capi.h"
 #include "octree.h"
+#include <mutex>
 #include "effects.h"
 #include "vm.h"
 
@@ -152,28 +153,52 @@ int32_t orc_render3d(const orc_tape* t, uint32_t w, uint32_t h, uint32_t d, cons
     });
 }
 
-// Octree sampler.  leaves: buffer of `cap` OctreeLeaf (348 bytes each) or NULL to count.
-int32_t orc_octree_sample(const orc_tape* t, uint32_t depth, const float* world_to_model16, void* leaves, uint64_t cap,
-                          uint64_t* n_leaves, uint64_t* stats /* [16*4 + 5] */) {
+// Octree sampler.  leaves: buffer of `cap` OctreeLeaf (348 bytes each) or NULL to count.  The result of
+// a counting call is kept, so that the fetching call that follows (same tape, depth, transform) copies it
+// instead of sampling again.
+static int32_t octree_sample_impl(const orc_tape* t, uint32_t depth, const float* world_to_model16, int threads, void* leaves,
+                                  uint64_t cap, uint64_t* n_leaves, uint64_t* stats) {
     ORC_TRY({
-        OctreeConfig cfg;
-        cfg.depth = depth;
-        if (world_to_model16) { cfg.has_transform = true; cfg.world_to_model = to_mat(world_to_model16); }
-        std::vector<OctreeLeaf> out;
-        OctreeStats st;
-        octree_sample(t->t, cfg, out, &st);
-        if (n_leaves) *n_leaves = out.size();
-        if (leaves) {
-            if (cap < out.size()) throw std::runtime_error("leaf buffer too small");
-            memcpy(leaves, out.data(), out.size() * sizeof(OctreeLeaf));
+        static std::mutex mu;
+        static std::vector<OctreeLeaf> last;
+        static OctreeStats last_st;
+        static const orc_tape* last_t = nullptr;
+        static uint32_t last_depth = 0;
+        static std::vector<float> last_m;
+        std::lock_guard<std::mutex> g(mu);
+        std::vector<float> m(world_to_model16 ? world_to_model16 : nullptr, world_to_model16 ? world_to_model16 + 16 : nullptr);
+        const bool reuse = leaves && last_t == t && last_depth == depth && last_m == m;
+        if (!reuse) {
+            OctreeConfig cfg;
+            cfg.depth = depth;
+            cfg.threads = threads;
+            if (world_to_model16) { cfg.has_transform = true; cfg.world_to_model = to_mat(world_to_model16); }
+            octree_sample(t->t, cfg, last, &last_st);
+            last_t = t; last_depth = depth; last_m = m;
         }
+        const OctreeStats& st = last_st;
+        if (n_leaves) *n_leaves = last.size();
         if (stats) {
             memcpy(stats, st.evaluated, 16 * 8); memcpy(stats + 16, st.full, 16 * 8);
             memcpy(stats + 32, st.empty, 16 * 8); memcpy(stats + 48, st.ambiguous, 16 * 8);
             stats[64] = st.leaf_empty; stats[65] = st.leaf_full; stats[66] = st.leaf_surface;
             stats[67] = st.float_points; stats[68] = st.grad_points;
         }
+        if (leaves) {
+            if (cap < last.size()) throw std::runtime_error("leaf buffer too small");
+            memcpy(leaves, last.data(), last.size() * sizeof(OctreeLeaf));
+            std::vector<OctreeLeaf>().swap(last);   // the fetch consumes the cached result
+            last_t = nullptr;
+        }
     });
+}
+int32_t orc_octree_sample(const orc_tape* t, uint32_t depth, const float* world_to_model16, void* leaves, uint64_t cap,
+                          uint64_t* n_leaves, uint64_t* stats /* [16*4 + 5] */) {
+    return octree_sample_impl(t, depth, world_to_model16, 1, leaves, cap, n_leaves, stats);
+}
+int32_t orc_octree_sample_mt(const orc_tape* t, uint32_t depth, const float* world_to_model16, int32_t threads, void* leaves,
+                             uint64_t cap, uint64_t* n_leaves, uint64_t* stats) {
+    return octree_sample_impl(t, depth, world_to_model16, threads, leaves, cap, n_leaves, stats);
 }
 static_assert(sizeof(OctreeLeaf) == 348, "OctreeLeaf layout");
 

@@ -2,6 +2,7 @@
 #include "octree.h"
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <stdexcept>
 #include <thread>
@@ -35,6 +36,7 @@ struct Builder {
     OctreeStats stats;
     std::vector<float> sx, sy, sz, sout;
     std::vector<Grad> gx, gy, gz, gout;
+    bool count_only = false;   // stop at cfg.depth without sampling leaves (census of the top levels)
 
     explicit Builder(const OctreeConfig& c) : cfg(c), sx(192), sy(192), sz(192), sout(192), gx(12), gy(12), gz(12), gout(12) {}
 
@@ -87,11 +89,32 @@ struct Builder {
             sub = h->simplify(trace);
         }
         if (depth == cfg.depth) {
-            leaf(sub, b, ix, iy, iz);
+            if (!count_only) leaf(sub, b, ix, iy, iz);
         } else {
             for (int c = 0; c < 8; ++c)
                 recurse(sub, child_bounds(b, c), depth + 1, 2 * ix + (c & 1), 2 * iy + ((c >> 1) & 1), 2 * iz + ((c >> 2) & 1));
         }
+    }
+
+    // One step of recurse() without statistics: the handle the children of this cell are evaluated with
+    // (alive = false when the cell is full or empty, i.e. has no children)
+    RenderHandle* descend(RenderHandle* h, const Bounds& b, bool& alive) {
+        const Tape& tape = *h->shape;
+        Interval xyz[3] = {b.b[0], b.b[1], b.b[2]};
+        if (cfg.has_transform) transform_interval(b.b[0], b.b[1], b.b[2], cfg.world_to_model, xyz);
+        Slots s = slots(tape);
+        Interval vars[3];
+        if (s.x >= 0) vars[s.x] = xyz[0];
+        if (s.y >= 0) vars[s.y] = xyz[1];
+        if (s.z >= 0) vars[s.z] = xyz[2];
+        Interval r;
+        bool has_trace = ieval.eval(tape, vars, &r);
+        if (r.hi < 0.0f || r.lo > 0.0f) { alive = false; return h; }
+        if (has_trace) {
+            std::vector<uint8_t> trace = ieval.choices;
+            return h->simplify(trace);
+        }
+        return h;
     }
 
     void leaf(RenderHandle* h, const Bounds& b, uint32_t ix, uint32_t iy, uint32_t iz) {
@@ -193,20 +216,83 @@ struct Builder {
 
 }  // namespace
 
-void octree_sample(const TapeP& tape, const OctreeConfig& cfg, std::vector<OctreeLeaf>& leaves, OctreeStats* stats) {
-    leaves.clear();
-    Bounds root;
-    for (int i = 0; i < 3; ++i) root.b[i] = Interval(-1.0f, 1.0f);   // CellBounds::new (cell.rs:146-150)
-    Builder b(cfg);
-    RenderHandle h(tape);
-    b.recurse(&h, root, 0, 0, 0, 0);
-    leaves = std::move(b.leaves);
+namespace {
+void sort_leaves(std::vector<OctreeLeaf>& leaves) {
     std::sort(leaves.begin(), leaves.end(), [](const OctreeLeaf& a, const OctreeLeaf& c) {
         if (a.iz != c.iz) return a.iz < c.iz;
         if (a.iy != c.iy) return a.iy < c.iy;
         return a.ix < c.ix;
     });
-    if (stats) *stats = b.stats;
+}
+void add_stats(OctreeStats& a, const OctreeStats& b) {
+    for (int i = 0; i < 16; ++i) {
+        a.evaluated[i] += b.evaluated[i]; a.full[i] += b.full[i]; a.empty[i] += b.empty[i]; a.ambiguous[i] += b.ambiguous[i];
+    }
+    a.leaf_empty += b.leaf_empty; a.leaf_full += b.leaf_full; a.leaf_surface += b.leaf_surface;
+    a.float_points += b.float_points; a.grad_points += b.grad_points;
+}
+}  // namespace
+
+// cfg.threads > 1: the counterpart of Octree::build_inner_mt (fidget-mesh/src/octree.rs:162-208), which hands
+// subtrees to worker threads.  Here every cell at depth SPLIT is a task; a worker walks the path from the
+// root to its cell first (same interval evaluations and simplifications as the serial descent, not
+// counted), then recurses below it with its own evaluators.  Leaves and statistics are the serial ones.
+void octree_sample(const TapeP& tape, const OctreeConfig& cfg, std::vector<OctreeLeaf>& leaves, OctreeStats* stats) {
+    leaves.clear();
+    Bounds root;
+    for (int i = 0; i < 3; ++i) root.b[i] = Interval(-1.0f, 1.0f);   // CellBounds::new (cell.rs:146-150)
+    const uint32_t SPLIT = 3;
+    if (cfg.threads <= 1 || cfg.depth <= SPLIT) {
+        Builder b(cfg);
+        RenderHandle h(tape);
+        b.recurse(&h, root, 0, 0, 0, 0);
+        leaves = std::move(b.leaves);
+        sort_leaves(leaves);
+        if (stats) *stats = b.stats;
+        return;
+    }
+    // serial census of depths < SPLIT (a shallow copy of the configuration that stops there)
+    OctreeStats total;
+    {
+        OctreeConfig top = cfg;
+        top.depth = SPLIT - 1;
+        Builder b(top);
+        b.count_only = true;
+        RenderHandle h(tape);
+        b.recurse(&h, root, 0, 0, 0, 0);
+        total = b.stats;
+    }
+    const uint32_t n_tasks = 1u << (3 * SPLIT);
+    std::atomic<uint32_t> next{0};
+    std::mutex mu;
+    std::vector<std::thread> pool;
+    for (int t = 0; t < cfg.threads; ++t)
+        pool.emplace_back([&]() {
+            Builder b(cfg);
+            for (;;) {
+                const uint32_t task = next.fetch_add(1);
+                if (task >= n_tasks) break;
+                // path: 3 bits per level, most significant level first
+                RenderHandle h(tape);
+                RenderHandle* cur = &h;
+                Bounds bb = root;
+                uint32_t ix = 0, iy = 0, iz = 0;
+                bool alive = true;
+                for (uint32_t d = 0; d < SPLIT && alive; ++d) {
+                    cur = b.descend(cur, bb, alive);
+                    const int c = int((task >> (3 * (SPLIT - 1 - d))) & 7u);
+                    bb = child_bounds(bb, c);
+                    ix = 2 * ix + (c & 1); iy = 2 * iy + ((c >> 1) & 1); iz = 2 * iz + ((c >> 2) & 1);
+                }
+                if (alive) b.recurse(cur, bb, SPLIT, ix, iy, iz);
+            }
+            std::lock_guard<std::mutex> g(mu);
+            leaves.insert(leaves.end(), b.leaves.begin(), b.leaves.end());
+            add_stats(total, b.stats);
+        });
+    for (auto& th : pool) th.join();
+    sort_leaves(leaves);
+    if (stats) *stats = total;
 }
 
 }  // namespace oracle

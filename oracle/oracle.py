@@ -260,17 +260,18 @@ OCTREE_LEAF = np.dtype([("ix", np.uint16), ("iy", np.uint16), ("iz", np.uint16),
                         ("pos", np.float32, (12, 3)), ("grad", np.float32, (12, 4))])
 
 
-def octree_sample(tape: Tape, depth: int, world_to_model=None):
-    """Sampler half of fidget-mesh's Octree::build: returns (leaves sorted by (iz,iy,ix), stats dict)."""
+def octree_sample(tape: Tape, depth: int, world_to_model=None, threads: int = 1):
+    """Sampler half of fidget-mesh's Octree::build: returns (leaves sorted by (iz,iy,ix), stats dict).
+    threads > 1 splits the tree into subtrees like Octree::build_inner_mt; the result is the serial one."""
     L = lib()
-    L.orc_octree_sample.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.c_void_p, C.c_uint64,
-                                    C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.orc_octree_sample_mt.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.c_int32, C.c_void_p, C.c_uint64,
+                                       C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     m = None if world_to_model is None else _fp(np.ascontiguousarray(world_to_model, dtype=np.float32).reshape(16))
     n = C.c_uint64()
     st = (C.c_uint64 * 69)()
-    _ck(L.orc_octree_sample(tape._h, depth, m, None, 0, C.byref(n), st))
+    _ck(L.orc_octree_sample_mt(tape._h, depth, m, threads, None, 0, C.byref(n), st))
     leaves = np.zeros(n.value, dtype=OCTREE_LEAF)
-    _ck(L.orc_octree_sample(tape._h, depth, m, leaves.ctypes.data_as(C.c_void_p), n.value, C.byref(n), st))
+    _ck(L.orc_octree_sample_mt(tape._h, depth, m, threads, leaves.ctypes.data_as(C.c_void_p), n.value, C.byref(n), st))
     s = list(st)
     stats = {"evaluated": s[0:16], "full": s[16:32], "empty": s[32:48], "ambiguous": s[48:64],
              "leaf_empty": s[64], "leaf_full": s[65], "leaf_surface": s[66], "float_points": s[67],

@@ -1,0 +1,296 @@
+"""The reference's own known-answer vectors (tests/golden/*.json, transcribed from
+fidget-core/src/eval/test/{interval,point,grad_slice,float_slice}.rs) pushed through the CUDA
+evaluators of the C ABI (fc_interval_eval, fc_point_eval, fc_float_slice_eval, fc_grad_slice_eval),
+plus a per-opcode sweep that reaches every op of dev_ops.cuh in its f32, interval and gradient form
+(register/register, register/immediate and immediate/register clauses).
+
+Tolerance classes: IEEE ops (add sub mul div sqrt neg abs square recip floor ceil round min max mod
+compare and or not rand mix) are bit-exact; ops that go through libm in the reference and libdevice
+here (sin cos tan asin acos atan atan2 exp ln) are within 1e-5 relative (north-star tolerance)."""
+import math
+import zlib
+
+import numpy as np
+import pytest
+
+import fidget_b200 as fb
+from fidget_b200.host import UNARY_OPS, BINARY_OPS
+from conftest import same_f32
+from test_oracle_goldens import IVL, POINT, GRD, CHOICE, _build, _f
+
+pytestmark = pytest.mark.gpu
+
+LIBM_OPS = {"sin", "cos", "tan", "asin", "acos", "atan", "atan2", "exp", "ln"}
+RTOL = 1e-5
+
+
+def _uses_libm(nodes):
+    return any(op in LIBM_OPS for _, op, _ in nodes)
+
+
+def _close(a, b):
+    """bitwise equal (NaN == NaN) or within the libm tolerance"""
+    a, b = np.asarray(a, dtype=np.float32), np.asarray(b, dtype=np.float32)
+    na, nb = np.isnan(a), np.isnan(b)
+    if not np.array_equal(na, nb):
+        return False
+    a, b = a[~na], b[~nb]
+    inf = np.isinf(b)
+    if not np.array_equal(a[inf], b[inf]):
+        return False
+    a, b = a[~inf].astype(np.float64), b[~inf].astype(np.float64)
+    return bool(np.all(np.abs(a - b) <= RTOL * np.maximum(1.0, np.abs(b))))
+
+
+@pytest.mark.parametrize("name", sorted(IVL))
+def test_interval_known_answers_cuda(cuda, name):
+    """eval/test/interval.rs through fc_interval_eval: exact bounds, exact Choice traces."""
+    spec = IVL[name]
+    ctx = fb.Context()
+    env = _build(ctx, spec["nodes"])
+    libm = _uses_libm(spec["nodes"])
+    shapes = {}
+    for case in spec["cases"]:
+        root = case["root"]
+        if root not in shapes:
+            td = ctx.tape(env[root])
+            shapes[root] = (td, fb.CudaShape(cuda, td))
+        td, g = shapes[root]
+        vx, vy, vz = td.var_slots()
+        ins = [[_f(a), _f(b)] for a, b in case["inputs"]]
+        vars_ = np.zeros((max(td.n_vars, 1), 2), dtype=np.float32)
+        for slot, iv in zip((vx, vy, vz), ins + [None] * 3):
+            if slot >= 0 and iv is not None:
+                vars_[slot] = iv
+        if td.n_vars == 1:
+            vars_[0] = ins[0]
+        out, choices, simplify = g.interval_eval(vars_)
+        out = out[0]
+        exp = [_f(v) for v in case["expect"]]
+        if any(isinstance(v, float) and math.isnan(v) for v in exp):
+            assert np.isnan(out).all(), (name, case)
+        elif libm:
+            assert _close(out, exp), (name, case, out)
+        else:
+            assert out.tolist() == [np.float32(exp[0]), np.float32(exp[1])], (name, case, out)
+        if "trace" in case:
+            if case["trace"] is None:
+                assert not simplify, (name, case)
+            else:
+                assert simplify and choices.tolist() == [CHOICE[c] for c in case["trace"]], (name, case)
+
+
+@pytest.mark.parametrize("name", sorted(POINT))
+def test_point_known_answers_cuda(cuda, name):
+    """eval/test/point.rs through fc_point_eval + fc_simplify: values, traces, simplified size."""
+    spec = POINT[name]
+    ctx = fb.Context()
+    env = _build(ctx, spec["nodes"])
+    td = ctx.tape(env[spec["root"]])
+    g = fb.CudaShape(cuda, td)
+    slots = list(td.var_slots()[:2])
+    libm = _uses_libm(spec["nodes"])
+
+    def run(shape, ins):
+        vars_ = np.zeros(max(td.n_vars, 1), dtype=np.float32)
+        if td.n_vars == 1 and ins:
+            vars_[0] = _f(ins[0])
+        else:
+            for slot, v in zip(slots, ins):
+                if slot >= 0:
+                    vars_[slot] = _f(v)
+        out, ch, s = shape.point_eval(vars_)
+        return out[0], ch, s
+
+    for case in spec["cases"]:
+        out, choices, simplify = run(g, case["inputs"])
+        exp = _f(case["expect"])
+        if isinstance(exp, float) and math.isnan(exp):
+            assert np.isnan(out), (name, case)
+        elif libm:
+            assert _close(out, exp), (name, case, out)
+        else:
+            assert out == np.float32(exp), (name, case, out)
+        if "trace" in case:
+            if case["trace"] is None:
+                assert not simplify, (name, case)
+            else:
+                assert simplify and choices.tolist() == [CHOICE[c] for c in case["trace"]], (name, case)
+        if "child_size" in case:
+            child = g.simplify(choices)
+            assert child.size() == case["child_size"], (name, child.size())
+            for cc in case["child_cases"]:
+                assert run(child, cc["inputs"])[0] == np.float32(cc["expect"])
+
+
+@pytest.mark.parametrize("name", sorted(GRD))
+def test_grad_known_answers_cuda(cuda, name):
+    """eval/test/grad_slice.rs through fc_grad_slice_eval."""
+    spec = GRD[name]
+    ctx = fb.Context()
+    env = _build(ctx, spec["nodes"])
+    libm = _uses_libm(spec["nodes"])
+    for case in spec["cases"]:
+        td = ctx.tape(env[case["root"]])
+        g = fb.CudaShape(cuda, td)
+        vx, vy, vz = td.var_slots()
+        vars_ = [np.zeros((1, 4), dtype=np.float32) for _ in range(max(td.n_vars, 1))]
+        for axis, slot in enumerate((vx, vy, vz)):
+            if slot >= 0:
+                vars_[slot][0, 0] = _f(case["xyz"][axis])
+                vars_[slot][0, 1 + axis] = 1.0
+        out = np.asarray(g.grad_slice_eval(vars_))[0]
+        exp = np.array([_f(v) for v in case["expect"]], dtype=np.float32)
+        if libm:
+            assert _close(out, exp), (name, case, out)
+        else:
+            assert np.array_equal(out, exp) or (np.isnan(exp).any() and np.array_equal(np.isnan(out), np.isnan(exp))), \
+                (name, case, out)
+
+
+def test_float_slice_vectorized_cuda(cuda):
+    """float_slice.rs:46-90 (test_vectorized) through fc_float_slice_eval: ragged slice lengths."""
+    ctx = fb.Context()
+    x, y = ctx.x(), ctx.y()
+    g = fb.CudaShape(cuda, ctx.tape(x))
+    for n in (4, 8, 9):
+        v = np.arange(n, dtype=np.float32)
+        assert g.float_slice_eval([v]).tolist() == v.tolist()
+    g = fb.CudaShape(cuda, ctx.tape(ctx.mul(y, 2.0)))
+    for ins, exp in (([3.0, 2.0, 1.0, 0.0], [6.0, 4.0, 2.0, 0.0]), ([1.0, 4.0, 8.0], [2.0, 8.0, 16.0]),
+                     ([1.0, 4.0, 4.0, -1.0, -2.0, -3.0, 0.0], [2.0, 8.0, 8.0, -2.0, -4.0, -6.0, 0.0])):
+        assert g.float_slice_eval([np.array(ins, dtype=np.float32)]).tolist() == exp
+
+
+# ---------------------------------------------------------------------------
+# Every opcode, every form (float_slice.rs:403-606 "canonical" suites in spirit: all ops over a grid
+# of special and ordinary values, here CUDA against the oracle instead of against std)
+SPECIAL = np.array([0.0, -0.0, 1.0, -1.0, 0.5, -0.5, 2.0, -2.0, 1.5, -1.5, 3.25, -7.75, 1e-3, -1e-3, 10.0, -10.0,
+                    100.0, 0.99999, -0.99999, 6.2831855, 3.1415927, 1.5707964, -3.1415927, 4.712389,
+                    1e-30, 1e30, np.inf, -np.inf, np.nan], dtype=np.float32)
+
+
+def _op_tapes(Ctx, op):
+    """(label, tape data) for every clause form of `op`: reg, reg/reg, reg/imm, imm/reg."""
+    out = []
+    if op in UNARY_OPS:
+        ctx = Ctx()
+        out.append(("r", ctx.tape(ctx.unary(op, ctx.x()))))
+    else:
+        ctx = Ctx()
+        out.append(("rr", ctx.tape(ctx.binary(op, ctx.x(), ctx.y()))))
+        for k in (0.75, -2.0, 0.0):
+            ctx = Ctx()
+            out.append((f"ri{k}", ctx.tape(ctx.binary(op, ctx.x(), ctx.constant(k)))))
+            ctx = Ctx()
+            out.append((f"ir{k}", ctx.tape(ctx.binary(op, ctx.constant(k), ctx.x()))))
+    return out
+
+
+@pytest.mark.parametrize("op", UNARY_OPS + BINARY_OPS)
+def test_every_op_f32_interval_grad(orc, cuda, op):
+    rng = np.random.default_rng(zlib.crc32(op.encode()))
+    exact = op not in LIBM_OPS
+    cmp = same_f32 if exact else _close
+    for (label, gtd), (_, otd) in zip(_op_tapes(fb.Context, op), _op_tapes(orc.Context, op)):
+        g, o = fb.CudaShape(cuda, gtd), orc.Tape.from_data(otd)
+        nv = max(gtd.n_vars, 1)
+        # ---- f32: the full grid of special values (pairs for two-variable tapes) + random points
+        if gtd.n_vars == 2:
+            xs, ys = [a.ravel() for a in np.meshgrid(SPECIAL, SPECIAL)]
+            pts = [np.concatenate([xs, rng.uniform(-3, 3, 257).astype(np.float32)]),
+                   np.concatenate([ys, rng.uniform(-3, 3, 257).astype(np.float32)])]
+        else:
+            pts = [np.concatenate([SPECIAL, rng.uniform(-3, 3, 257).astype(np.float32)])] * nv
+        gv, ov = np.asarray(g.float_slice_eval(pts)), o.float_slice_eval(pts)
+        assert cmp(gv, ov), (op, label, "f32", gv[:8], ov[:8])
+        # ---- point evaluation with choices (min/max/and/or)
+        if gtd.choice_count:
+            for i in range(0, len(pts[0]), 7):
+                v = np.array([p[i] for p in pts], dtype=np.float32)
+                go, gc, gs = g.point_eval(v)
+                oo, oc, os_ = o.point_eval(v)
+                assert cmp(go[0], oo) and np.array_equal(gc, oc) and gs == os_, (op, label, "point", v)
+        # ---- intervals: boxes with special endpoints, point intervals, wide and narrow random boxes
+        n = 400
+        lo = rng.choice(SPECIAL[:-1], (n, nv))
+        hi = rng.choice(SPECIAL[:-1], (n, nv))
+        lo, hi = np.minimum(lo, hi), np.maximum(lo, hi)
+        c = rng.uniform(-3, 3, (n, nv)).astype(np.float32)
+        w = (rng.uniform(0, 1, (n, nv)) ** 3 * 4).astype(np.float32)
+        boxes = np.concatenate([np.stack([lo, hi], -1), np.stack([c - w, c + w], -1), np.stack([c, c], -1)]).astype(np.float32)
+        boxes[::37, 0, :] = np.nan                      # NaN intervals propagate
+        gout, gch, gsimp = g.interval_eval_batch(boxes, want_choices=True)
+        for i in range(boxes.shape[0]):
+            oo, oc, os_ = o.interval_eval(boxes[i])
+            assert cmp(gout[i, 0], oo), (op, label, "interval", boxes[i], gout[i, 0], oo)
+            assert np.array_equal(gch[i], oc) and bool(gsimp[i]) == os_, (op, label, "choices", boxes[i])
+        # ---- gradients
+        m = 300
+        vars_ = []
+        for k in range(nv):
+            a = np.zeros((m, 4), dtype=np.float32)
+            a[:, 0] = np.concatenate([rng.choice(SPECIAL, 60), rng.uniform(-3, 3, m - 60)])
+            a[:, 1 + k] = 1.0
+            a[:, 1:] += rng.uniform(-1, 1, (m, 3)).astype(np.float32) * (rng.random((m, 1)) < 0.5)
+            vars_.append(a)
+        gg, og = np.asarray(g.grad_slice_eval(vars_)), o.grad_slice_eval(vars_)
+        assert cmp(gg, og), (op, label, "grad")
+
+
+def _random_expr(ctx, rng, depth, ops_u, ops_b):
+    """A random expression tree over x, y, z drawing from every opcode."""
+    if depth == 0 or rng.random() < 0.15:
+        r = rng.random()
+        if r < 0.25:
+            return ctx.constant(float(np.float32(rng.uniform(-2, 2))))
+        return [ctx.x, ctx.y, ctx.z][int(rng.integers(0, 3))]()
+    if rng.random() < 0.4:
+        return ctx.unary(ops_u[int(rng.integers(0, len(ops_u)))], _random_expr(ctx, rng, depth - 1, ops_u, ops_b))
+    return ctx.binary(ops_b[int(rng.integers(0, len(ops_b)))], _random_expr(ctx, rng, depth - 1, ops_u, ops_b),
+                      _random_expr(ctx, rng, depth - 1, ops_u, ops_b))
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_expressions_all_ops(orc, cuda, seed):
+    """Random trees through the four evaluators.  Even seeds draw every IEEE-exact opcode (including the
+    discontinuous ones: floor ceil round compare mod not and or rand mix) and must agree bit for bit --
+    values, interval bounds, choice traces, gradients.  Odd seeds draw the libm opcodes together with the
+    continuous exact ones (a discontinuous op downstream of a 1-ulp libm difference would legitimately
+    diverge); there >= 97% of the points must agree within 1e-4 relative (ulp differences are amplified by
+    divisions and cancellations in a random tree)."""
+    exact = seed % 2 == 0
+    CONT = {"neg", "abs", "recip", "sqrt", "square", "add", "sub", "mul", "div", "min", "max"}
+    ops_u = [o for o in UNARY_OPS if (o not in LIBM_OPS if exact else (o in LIBM_OPS or o in CONT))]
+    ops_b = [o for o in BINARY_OPS if (o not in LIBM_OPS if exact else (o in LIBM_OPS or o in CONT))]
+    tapes = []
+    for Ctx in (fb.Context, orc.Context):
+        ctx = Ctx()
+        rng = np.random.default_rng(7000 + seed)
+        roots = _random_expr(ctx, rng, 6, ops_u, ops_b)
+        tapes.append(ctx.tape(roots))
+    g, o = fb.CudaShape(cuda, tapes[0]), orc.Tape.from_data(tapes[1])
+    nv = max(tapes[0].n_vars, 1)
+    rng = np.random.default_rng(seed)
+    pts = [rng.uniform(-2, 2, 2048).astype(np.float32) for _ in range(nv)]
+    gv, ov = np.asarray(g.float_slice_eval(pts)), o.float_slice_eval(pts)
+    if exact:
+        assert same_f32(gv, ov)
+    else:
+        ok = (np.isnan(gv) & np.isnan(ov)) | (np.abs(gv.astype(np.float64) - ov) <= 1e-4 * np.maximum(1, np.abs(ov))) | (gv == ov)
+        assert ok.mean() >= 0.97, ok.mean()
+    c = rng.uniform(-2, 2, (256, nv)).astype(np.float32)
+    w = (rng.uniform(0, 1, (256, nv)) ** 2).astype(np.float32)
+    boxes = np.stack([c - w, c + w], -1).astype(np.float32)
+    gout, gch, gsimp = g.interval_eval_batch(boxes, want_choices=True)
+    if exact:
+        for i in range(boxes.shape[0]):
+            oo, oc, os_ = o.interval_eval(boxes[i])
+            assert same_f32(gout[i, 0], oo) and np.array_equal(gch[i], oc) and bool(gsimp[i]) == os_, (seed, i)
+        vars_ = []
+        for k in range(nv):
+            a = np.zeros((512, 4), dtype=np.float32)
+            a[:, 0] = pts[k][:512]
+            a[:, 1 + (k % 3)] = 1.0
+            vars_.append(a)
+        assert same_f32(np.asarray(g.grad_slice_eval(vars_)), o.grad_slice_eval(vars_))

@@ -311,6 +311,47 @@ def test_spilled_tapes_evaluate_like_the_oracle(orc, cuda, name):
         fb.render2d(gs, fb.RenderConfig2D(64, 64))
 
 
+def test_tape_using_all_255_registers(orc, cuda):
+    """reg_count == 255 is the reference's VmData<255> (registers 0..254): such tapes -- every spilling tape
+    at the default register count -- must upload and evaluate like the oracle."""
+    tapes = []
+    for Ctx in (fb.Context, orc.Context):
+        ctx = Ctx()
+        x, y, z = ctx.x(), ctx.y(), ctx.z()
+        s = ctx.constant(0.0)
+        inputs = []
+        for i in range(1, 301):                       # 300 values live across the sin: more than 255 registers
+            d = ctx.mul(ctx.constant(float(i)), [x, y, z][i % 3])
+            inputs.append(d)
+            s = ctx.add(s, d)
+        s = ctx.sin(s)
+        for d in reversed(inputs):
+            s = ctx.min(ctx.add(s, d), ctx.mul(d, 0.5))
+        tapes.append(ctx.tape(s))
+    gs, ot = fb.CudaShape(cuda, tapes[0]), orc.Tape.from_data(tapes[1])
+    assert gs.info.reg_count == 255 and gs.info.mem_count > 0
+    pts = _points(1025, 3, 5)
+    g, o = np.asarray(gs.float_slice_eval(pts)), ot.float_slice_eval(pts)
+    assert np.allclose(g, o, rtol=1e-5, atol=1e-5, equal_nan=True)          # one sin: libm tolerance
+    boxes = _boxes(33, 3, 9, scale=0.05)
+    out, ch, simp = gs.interval_eval_batch(boxes, want_choices=True)
+    for i in range(boxes.shape[0]):
+        o, oc, os_ = ot.interval_eval(boxes[i])
+        assert np.allclose(out[i, 0], o, rtol=1e-5, atol=1e-4, equal_nan=True)
+    with pytest.raises(fb.CudaError):
+        fb.render2d(gs, fb.RenderConfig2D(64, 64))
+
+
+def test_render2d_band_leaves_other_rows_untouched(orc, cuda):
+    """A band render into a HOST image writes the rows of its band and nothing else."""
+    ot, gs = _pair(orc, cuda, "hi.vm")
+    want, _ = orc.render2d(ot, 512, 512)
+    img = np.full((512, 512), 123.0, dtype=np.float32)
+    fb.render2d(gs, fb.RenderConfig2D(512, 512, root_rows=(1, 3)), out=img)
+    assert np.all(img[:128] == 123.0) and np.all(img[384:] == 123.0)
+    assert np.array_equal(img[128:384].view(np.uint32), want[128:384].view(np.uint32))
+
+
 def test_grad_slice_matches_oracle(orc, cuda):
     for name, exact in (("prospero.vm", True), ("colonnade.vm", True), ("bear.vm", False)):
         ot, gs = _pair(orc, cuda, name)
@@ -440,7 +481,7 @@ def test_render2d_ragged_sizes(orc, cuda, w, h):
     assert g_st["evaluated"] == o_st["evaluated"] and g_st["pixels"] == o_st["pixels"]
 
 
-@pytest.mark.parametrize("ts", [(128, 16), (64, 8), (256, 32, 8), (8,)])
+@pytest.mark.parametrize("ts", [(128, 16), (64, 8), (256, 32, 8), (8,), (96, 24, 6), (48, 12), (100, 20, 5), (36, 6, 3)])
 def test_render2d_custom_tile_sizes(orc, cuda, ts):
     # EvalConfig::tile_sizes (pixel.rs:42-57); (128, 16) is the JIT's default (fidget-jit/src/lib.rs:984)
     ot, gs = _pair(orc, cuda, "prospero.vm")

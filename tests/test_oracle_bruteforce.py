@@ -171,3 +171,18 @@ def test_octree_edge_intersections_bracket_the_surface(orc):
             if (int(l["present"]) >> e) & 1:
                 g, p = l["grad"][e][:3].astype(np.float64), l["pos"][e].astype(np.float64)
                 assert np.allclose(g / np.linalg.norm(g), p / np.linalg.norm(p), atol=1e-4)
+
+
+def test_octree_threads_do_not_change_the_result(orc):
+    """The multi-threaded oracle sampler (subtrees on worker threads, like Octree::build_inner_mt) returns
+    the serial leaves and census, byte for byte."""
+    t = orc.Tape.from_vm(model_text("gyroid-sphere.vm"))
+    a, sa = orc.octree_sample(t, 5)
+    b, sb = orc.octree_sample(t, 5, threads=4)
+    assert sa == sb and a.tobytes() == b.tobytes()
+    m = np.eye(4, dtype=np.float32)
+    m[0, 3], m[1, 1] = 0.1, 1.2
+    t = orc.Tape.from_vm(model_text("colonnade.vm"))
+    a, sa = orc.octree_sample(t, 4, m)
+    b, sb = orc.octree_sample(t, 4, m, threads=3)
+    assert sa == sb and a.tobytes() == b.tobytes()
