@@ -39,7 +39,8 @@ class FcRender2dCfg(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("mat", C.c_float * 16), ("z", C.c_float),
                 ("pixel_perfect", C.c_uint32), ("n_tile_sizes", C.c_uint32), ("tile_sizes", C.c_uint32 * 8),
                 ("flags", C.c_uint32), ("root_row_begin", C.c_uint32), ("root_row_end", C.c_uint32),
-                ("n_var_values", C.c_uint32), ("var_values", C.c_float * 16)]
+                ("n_var_values", C.c_uint32), ("var_values", C.c_float * 16),
+                ("root_stride", C.c_uint32), ("root_offset", C.c_uint32), ("out_format", C.c_uint32)]
 
 
 class FcScheduleInfo(C.Structure):
@@ -51,7 +52,8 @@ class FcRender3dCfg(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("depth", C.c_uint32), ("mat", C.c_float * 16),
                 ("n_tile_sizes", C.c_uint32), ("tile_sizes", C.c_uint32 * 8), ("flags", C.c_uint32),
                 ("z_begin", C.c_uint32), ("z_end", C.c_uint32), ("n_var_values", C.c_uint32),
-                ("var_values", C.c_float * 16), ("root_row_begin", C.c_uint32), ("root_row_end", C.c_uint32)]
+                ("var_values", C.c_float * 16), ("root_row_begin", C.c_uint32), ("root_row_end", C.c_uint32),
+                ("root_stride", C.c_uint32), ("root_offset", C.c_uint32)]
 
 
 class FcRenderStats(C.Structure):
@@ -90,6 +92,7 @@ class FcOctreeStats(C.Structure):
 FC_FLAG_ASYNC = 1
 FC_FLAG_TIMING = 2
 FC_FLAG_NO_CLAMP = 4
+FC_OUT_F32, FC_OUT_MASK_U8, FC_OUT_BITMAP_1BIT, FC_OUT_RGBA8 = 0, 1, 2, 3
 
 # name -> (restype, argtypes); mirrors include/fidget_cuda.h one to one
 _vp, _u32, _i32, _u64, _u8 = C.c_void_p, C.c_uint32, C.c_int32, C.c_uint64, C.c_uint8
@@ -119,6 +122,9 @@ CUDA_API = {
     "fc_render2d": (_i32, [_vp, _vp, _P(FcRender2dCfg), _vp, _P(FcRenderStats)]),
     "fc_render3d": (_i32, [_vp, _vp, _P(FcRender3dCfg), _vp, _P(FcRenderStats)]),
     "fc_merge_slabs": (_i32, [_vp, _P(_vp), _u32, _u32, _u32, _u32, _vp]),
+    "fc_tiles_per_rank": (_u32, [_u32, _u32, _u32, _u32]),
+    "fc_tiles_pack": (_i32, [_vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp]),
+    "fc_tiles_unpack": (_i32, [_vp, _vp, _u32, _u32, _u32, _u32, _u32, _vp]),
     "fc_octree_sample": (_i32, [_vp, _vp, _P(FcOctreeCfg), _vp, _u64, _P(_u64), _P(FcOctreeStats)]),
     "fc_schedule_check": (_i32, [_P(_u32), C.c_size_t, _u8, _u32, _u32, _u32, _P(FcScheduleInfo)]),
     "fc_denoise_normals": (_i32, [_vp, _vp, _u32, _u32, _vp]),

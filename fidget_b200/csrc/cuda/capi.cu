@@ -77,7 +77,7 @@ static void to_bytecode(const std::vector<uint2>& cl, std::vector<uint32_t>& wor
 extern "C" {
 
 const char* fc_last_error(void) { return g_err.c_str(); }
-uint32_t fc_abi_version(void) { return 1; }
+uint32_t fc_abi_version(void) { return 2; }
 
 int32_t fc_ctx_create(int32_t device, fc_ctx** out) {
     if (!out) return fail(FC_ERR_INVALID, "null out");
@@ -123,6 +123,8 @@ void fc_ctx_destroy(fc_ctx* c) {
     c->heightmap.release();
     c->leaf_tapes.release();
     c->zsort.release();
+    c->root_list.release();
+    c->tile_slots.release();
     c->fx_in.release();
     c->fx_out.release();
     c->fx_tmp.release();
@@ -388,7 +390,20 @@ static int32_t bulk_eval(fc_eval* e, const fc_tape* t, const void* const* vars, 
     p.n = n;
     p.vars = e->ptrs.as<const void*>();
     p.outs = reinterpret_cast<void* const*>(e->ptrs.as<void*>() + nv);
-    if (grad) launch_grad_slice(p, c->stream); else launch_float_slice(p, c->stream);
+    bool fast = false;
+    if (!t->info.mem_count && n >= 4096 && nv <= 4 && no <= 2 && !env_int("FIDGET_B200_NO_TMA", 0)) {
+        SliceTmaParams q{};
+        q.tape = t->dev;
+        q.n_ops = t->info.n_ops;
+        q.n_vars = nv;
+        q.n_outputs = no;
+        q.n_regs = t->info.reg_count;
+        q.n = n;
+        for (uint32_t i = 0; i < nv; ++i) q.vars[i] = static_cast<const float4*>(dptr[i]);
+        for (uint32_t o = 0; o < no; ++o) q.outs[o] = static_cast<float4*>(const_cast<void*>(dptr[nv + o]));
+        fast = launch_slice_tma(q, grad, c->sm_count, c->stream);
+    }
+    if (!fast) { if (grad) launch_grad_slice(p, c->stream); else launch_float_slice(p, c->stream); }
     CU(cudaGetLastError());
     for (auto& cb : copy_back)
         if (n) CU(cudaMemcpyAsync(cb.first, cb.second, n * elem, cudaMemcpyDeviceToHost, c->stream));

@@ -91,6 +91,11 @@ struct fc_ctx {
     // render scratch
     DevBuf arena, jobs[MAX_LEVELS + 1], fills[MAX_LEVELS], choice_scratch, counters, stats, image, heightmap, leaf_tapes, zsort;
     DevBuf fx_in, fx_out, fx_tmp, fx_tables;  // effects: staged host images, intermediate maps, SSAO tables
+    // tile interleave: device list of this rank's XY root tiles (cached on its key), and the
+    // tile -> gathered-slot table of fc_tiles_unpack
+    DevBuf root_list, tile_slots;
+    uint32_t root_list_key[5] = {0, 0, 0, 0, 0}, root_list_n = 0;
+    uint32_t tile_slots_key[4] = {0, 0, 0, 0};
     std::vector<cudaEvent_t> events;
     std::mutex mu;
     // tape uploads: released device buffers are reused (no cudaMalloc / cudaFree per tape) and the
@@ -152,3 +157,5 @@ int32_t pick_tile_sizes(const uint32_t* ts_in, uint32_t n_in, const uint32_t* df
                         std::vector<uint32_t>& ts);
 int32_t bind_vars(const fc_tape* t, const float* values, uint32_t n_values, VarBind& vb);
 cudaEvent_t get_event(fc_ctx* c, size_t i);
+int32_t root_subset(fc_ctx* c, uint32_t roots_x, uint32_t row0, uint32_t row1, uint32_t stride, uint32_t offset,
+                    cudaStream_t s, const uint32_t** d_list, uint32_t* n);

@@ -60,7 +60,7 @@ k_interval_root_coop(const __grid_constant__ LevelParams p) {
     const CoopRec* __restrict__ recs = p.sched.recs;
     const CoopFwd* __restrict__ fwd = p.sched.fwd;
     const uint32_t* __restrict__ ws = p.sched.wave_start;
-    const uint32_t n_roots = p.roots_x * p.roots_y * (DIM == 3 ? p.roots_z : 1u);
+    const uint32_t n_roots = root_count(p, DIM == 3);
     const uint2* __restrict__ tape = p.root_tape.ptr;
 
     for (;;) {
@@ -75,8 +75,9 @@ k_interval_root_coop(const __grid_constant__ LevelParams p) {
         __syncthreads();
         const uint32_t tile = s_tile;
         if (tile >= n_roots) break;
-        const uint32_t cx = p.root_x0 + (tile % p.roots_x) * T, cy = p.root_y0 + ((tile / p.roots_x) % p.roots_y) * T;
-        const uint32_t cz = DIM == 3 ? p.root_z0 + (tile / (p.roots_x * p.roots_y)) * T : 0u;
+        uint32_t cx, cy, cz;
+        root_corner(p, tile, T, cx, cy, cz);
+        if (DIM != 3) cz = 0u;
         itv vx, vy, vz;
         xform_iv(p.mat, iv(float(cx), float(cx) + float(T)), iv(float(cy), float(cy) + float(T)),
                  DIM == 3 ? iv(float(cz), float(cz) + float(T)) : iv(p.z2d, p.z2d), vx, vy, vz);

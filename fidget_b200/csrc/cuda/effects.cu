@@ -356,6 +356,33 @@ void launch_apply_shading(const GeoPixel* img, uint32_t w, uint32_t h, uint32_t 
 void launch_normals_to_color(const GeoPixel* img, uint64_t n, uint8_t* out, cudaStream_t s) {
     k_normals_to_color<<<unsigned((n + 255) / 256), 256, 0, s>>>(img, n, out);
 }
+// Inside/outside masks of a RawDistancePixel image (RawDistancePixel::inside, pixel.rs:177-183): one warp per
+// 32 consecutive pixels of a row; the ballot IS the 1-bit packing (bit x%8 of byte x/8, LSB first).
+__global__ void __launch_bounds__(256) k_to_mask(const float* __restrict__ img, uint32_t w, uint32_t h, uint8_t* __restrict__ out,
+                                                 int one_bit, uint32_t stride) {
+    const uint32_t words = (w + 31u) / 32u;
+    const uint64_t warp = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= uint64_t(words) * h) return;
+    const uint32_t y = uint32_t(warp / words), x = uint32_t(warp % words) * 32u + (threadIdx.x & 31u);
+    bool inside = false;
+    if (x < w) {
+        const float f = __ldg(img + size_t(y) * w + x);
+        inside = is_distance(f) ? (f < 0.0f) : ((__float_as_uint(f) & 1u) == 1u);
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, inside);
+    if (one_bit) {
+        const uint32_t lane = threadIdx.x & 31u;
+        if (lane < 4u && x - lane + lane * 8u < w) out[size_t(y) * stride + (x - lane) / 8u + lane] = uint8_t(m >> (8u * lane));
+    } else if (x < w) {
+        out[size_t(y) * w + x] = inside ? 255 : 0;
+    }
+}
+void launch_to_mask(const float* img, uint32_t w, uint32_t h, uint8_t* out, int one_bit, cudaStream_t s) {
+    const uint64_t warps = uint64_t((w + 31u) / 32u) * h;
+    if (!warps) return;
+    k_to_mask<<<unsigned((warps * 32 + 255) / 256), 256, 0, s>>>(img, w, h, out, one_bit, (w + 7u) / 8u);
+}
+
 void launch_to_rgba(int mode, const float* img, uint64_t n, uint8_t* out, cudaStream_t s) {
     const int vec4 = (reinterpret_cast<uintptr_t>(img) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
     const uint64_t threads = vec4 ? (n + 3) / 4 : n;

@@ -18,6 +18,8 @@ void launch_apply_shading(const GeoPixel* img, uint32_t w, uint32_t h, uint32_t 
                           uint8_t* out_rgb, cudaStream_t s);
 void launch_normals_to_color(const GeoPixel* img, uint64_t n, uint8_t* out_rgb, cudaStream_t s);
 // mode 0: to_rgba_bitmap, 1: to_rgba_bitmap(transparent), 2: to_debug_bitmap, 3: to_rgba_distance
+// inside/outside mask: one byte (255 / 0) per pixel, or one bit per pixel (rows padded to whole bytes)
+void launch_to_mask(const float* img, uint32_t w, uint32_t h, uint8_t* out, int one_bit, cudaStream_t s);
 void launch_to_rgba(int mode, const float* img, uint64_t n, uint8_t* out_rgba, cudaStream_t s);
 
 }  // namespace fdev

@@ -41,7 +41,7 @@ k_interval_level(const __grid_constant__ LevelParams p) {
     uint32_t* cs = p.choice_scratch + size_t(gw) * p.choice_words * 32u + lane;
     itv slots[REG_SLOTS];
 
-    const uint32_t n_roots = p.roots_x * p.roots_y * (DIM == 3 ? p.roots_z : 1u);
+    const uint32_t n_roots = root_count(p, DIM == 3);
     const uint32_t n_jobs = p.root_mode ? (n_roots + 31u) / 32u : min(p.ctr->n_jobs[p.level], p.cap_in);
     const uint32_t T = p.tile;
 
@@ -71,10 +71,7 @@ k_interval_level(const __grid_constant__ LevelParams p) {
             const bool valid = c < nchild;
             uint32_t cx, cy, cz = 0;
             if (p.root_mode) {
-                uint32_t idx = j * 32u + (valid ? c : 0u);
-                cx = p.root_x0 + (idx % p.roots_x) * T;
-                cy = p.root_y0 + ((idx / p.roots_x) % p.roots_y) * T;
-                if (DIM == 3) cz = p.root_z0 + (idx / (p.roots_x * p.roots_y)) * T;
+                root_corner(p, j * 32u + (valid ? c : 0u), T, cx, cy, cz);
             } else {
                 uint32_t cc = valid ? c : 0u;
                 cx = px + (cc % p.n_axis) * T;
@@ -342,9 +339,19 @@ __global__ void __launch_bounds__(128) k_normals_3d(const __grid_constant__ Norm
     const int lane = threadIdx.x & 31;
     // 8x4 pixel patch per warp
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t patches_x = (p.width + 7u) / 8u, patches_y = (p.y1 - p.y0 + 3u) / 4u;
-    if (warp >= patches_x * patches_y) return;
-    const uint32_t x = (warp % patches_x) * 8u + (lane & 7), y = p.y0 + (warp / patches_x) * 4u + (lane >> 3);
+    uint32_t x, y;
+    if (p.root_list) {   // patches of the listed root tiles only
+        const uint32_t ppt = (p.root_tile / 8u) * (p.root_tile / 4u), ppr = p.root_tile / 8u;
+        if (warp >= p.n_root_list * ppt) return;
+        const uint32_t id = __ldg(p.root_list + warp / ppt), q = warp % ppt;
+        x = (id % p.roots_x) * p.root_tile + (q % ppr) * 8u + (lane & 7);
+        y = p.y0 + (id / p.roots_x) * p.root_tile + (q / ppr) * 4u + (lane >> 3);
+    } else {
+        const uint32_t patches_x = (p.width + 7u) / 8u, patches_y = (p.y1 - p.y0 + 3u) / 4u;
+        if (warp >= patches_x * patches_y) return;
+        x = (warp % patches_x) * 8u + (lane & 7);
+        y = p.y0 + (warp / patches_x) * 4u + (lane >> 3);
+    }
     const bool inb = x < p.width && y < p.y1;
     const unsigned long long key = inb ? p.heightmap[size_t(y) * p.width + x] : 0ull;
     const uint32_t depth = uint32_t(key >> 32), id = uint32_t(key);
@@ -381,7 +388,8 @@ __global__ void __launch_bounds__(128) k_normals_3d(const __grid_constant__ Norm
     }
 }
 void launch_normals_3d(const NormalParams& p, cudaStream_t s) {
-    const uint64_t warps = uint64_t((p.width + 7u) / 8u) * ((p.y1 - p.y0 + 3u) / 4u);
+    const uint64_t warps = p.root_list ? uint64_t(p.n_root_list) * (p.root_tile / 8u) * (p.root_tile / 4u)
+                                       : uint64_t((p.width + 7u) / 8u) * ((p.y1 - p.y0 + 3u) / 4u);
     if (!warps) return;
     k_normals_3d<<<unsigned((warps + 3) / 4), 128, 0, s>>>(p);
 }
@@ -404,6 +412,36 @@ void launch_merge_slabs(const void* const* d_slabs, uint32_t n_slabs, uint32_t n
                         cudaStream_t s) {
     k_merge_slabs<<<(n_pixels + 255) / 256, 256, 0, s>>>(reinterpret_cast<const float4* const*>(d_slabs), n_slabs,
                                                          n_pixels, depth, reinterpret_cast<float4*>(out));
+}
+
+// Multi-GPU tile interleave: image <-> [slot][T][T] chunks.  One CTA per (tile, 8 rows); consecutive threads
+// move consecutive pixels of a row, so both sides are coalesced (16-byte pixels move as one float4).
+template <class PX>
+__global__ void __launch_bounds__(256) k_tiles_copy(const PX* __restrict__ src, PX* __restrict__ dst, uint32_t width,
+                                                    uint32_t height, uint32_t T, uint32_t roots_x, const uint32_t* __restrict__ slots,
+                                                    uint32_t n_ranks, uint32_t per_rank, int rank) {
+    const uint32_t tile = blockIdx.x, tx = tile % roots_x, ty = tile / roots_x;
+    if (rank >= 0 && (tx + ty) % n_ranks != uint32_t(rank)) return;
+    const uint32_t slot = slots[tile];
+    const size_t chunk = size_t(rank >= 0 ? slot - uint32_t(rank) * per_rank : slot) * T * T;
+    for (uint32_t q = blockIdx.y * 8u * T + threadIdx.x; q < min((blockIdx.y + 1u) * 8u, T) * T; q += blockDim.x) {
+        const uint32_t x = tx * T + q % T, y = ty * T + q / T;
+        if (x >= width || y >= height) continue;
+        const size_t img = size_t(y) * width + x;
+        if (rank >= 0) dst[chunk + q] = src[img];
+        else dst[img] = src[chunk + q];
+    }
+}
+void launch_tiles_copy(const void* src, void* dst, uint32_t width, uint32_t height, uint32_t px_bytes, uint32_t T,
+                       uint32_t roots_x, uint32_t roots_y, const uint32_t* slots, uint32_t n_ranks, uint32_t per_rank, int rank,
+                       cudaStream_t s) {
+    const dim3 grid(roots_x * roots_y, (T + 7u) / 8u);
+    if (px_bytes == 16)
+        k_tiles_copy<float4><<<grid, 256, 0, s>>>(static_cast<const float4*>(src), static_cast<float4*>(dst), width, height, T,
+                                                  roots_x, slots, n_ranks, per_rank, rank);
+    else
+        k_tiles_copy<float><<<grid, 256, 0, s>>>(static_cast<const float*>(src), static_cast<float*>(dst), width, height, T,
+                                                 roots_x, slots, n_ranks, per_rank, rank);
 }
 
 // ---------------------------------------------------------------------------

@@ -110,6 +110,10 @@ struct LevelParams {
     uint32_t root_mode;
     uint32_t roots_x, roots_y, roots_z;     // root grid
     uint32_t root_x0, root_y0, root_z0;     // origin of the root grid (pixels)
+    // multi-GPU tile interleave: when non-null only the XY root tiles listed here (ty * roots_x + tx inside
+    // the band) are evaluated, at every Z layer
+    const uint32_t* root_list;
+    uint32_t n_root_list;
     TapeRef root_tape;
     // image
     uint32_t width, height, depth;
@@ -138,6 +142,23 @@ struct LevelParams {
     unsigned long long* heightmap;  // 3D: width*height keys (depth << 32 | leaf job id + 1), atomicMax
     VarBind vb;
 };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t root_count(const LevelParams& p, bool with_z) {
+    return (p.root_list ? p.n_root_list : p.roots_x * p.roots_y) * (with_z ? p.roots_z : 1u);
+}
+// corner of root tile `idx` (XY-major, then Z layers)
+__device__ __forceinline__ void root_corner(const LevelParams& p, uint32_t idx, uint32_t T, uint32_t& cx, uint32_t& cy,
+                                            uint32_t& cz) {
+    const uint32_t n_xy = p.root_list ? p.n_root_list : p.roots_x * p.roots_y;
+    uint32_t xy = idx % n_xy;
+    const uint32_t zl = idx / n_xy;
+    if (p.root_list) xy = __ldg(p.root_list + xy);
+    cx = p.root_x0 + (xy % p.roots_x) * T;
+    cy = p.root_y0 + (xy / p.roots_x) * T;
+    cz = p.root_z0 + zl * T;
+}
+#endif
 
 struct PixelParams {
     uint32_t tile;             // leaf tile edge
@@ -175,6 +196,9 @@ struct VoxelParams {
 struct NormalParams {
     uint32_t width, height, depth;
     uint32_t y0, y1;            // rows to finish (a Y band of a sharded render, else 0..height)
+    // tile interleave: only these root tiles (ty * roots_x + tx inside the band, edge `root_tile`) are finished
+    const uint32_t* root_list;
+    uint32_t n_root_list, roots_x, root_tile;
     uint32_t clamp;             // apply the final `depth >= D-1` clamp (voxel.rs:535-546)
     Mat4 mat;
     const TileJob* jobs;        // leaf jobs
@@ -219,6 +243,11 @@ void launch_leaf_zsort(const TileJob* jobs, const uint32_t* n_jobs, uint32_t cap
 void launch_normals_3d(const NormalParams& p, cudaStream_t s);
 void launch_merge_slabs(const void* const* d_slabs, uint32_t n_slabs, uint32_t n_pixels, uint32_t depth, void* out,
                         cudaStream_t s);
+// tile interleave: rank >= 0 packs that rank's tiles of `src` (an image) into `dst` (its chunk);
+// rank < 0 unpacks every tile of the gathered chunks in `src` into the image `dst`
+void launch_tiles_copy(const void* src, void* dst, uint32_t width, uint32_t height, uint32_t px_bytes, uint32_t T,
+                       uint32_t roots_x, uint32_t roots_y, const uint32_t* slots, uint32_t n_ranks, uint32_t per_rank, int rank,
+                       cudaStream_t s);
 void launch_interval_level_2d(const LevelParams& p, int blocks, cudaStream_t s);
 int coop_regs_per_thread(int dim);
 int coop_occupancy(int dim, int threads, size_t smem);
@@ -239,6 +268,16 @@ struct BulkParams {
     void* const* outs;          // device array of device pointers (n_outputs)
 };
 void launch_float_slice(const BulkParams& p, cudaStream_t s);
+// TMA-fed persistent bulk evaluators (bulk.cu): float4 columns, i.e. four consecutive f32 points or one
+// gradient per thread
+struct SliceTmaParams {
+    const uint2* tape;
+    uint32_t n_ops, n_vars, n_outputs, n_regs;
+    uint64_t n;                 // points
+    const float4* vars[4];
+    float4* outs[2];
+};
+bool launch_slice_tma(const SliceTmaParams& p, bool grad, int sm_count, cudaStream_t s);
 void launch_grad_slice(const BulkParams& p, cudaStream_t s);
 
 struct TracingParams {

@@ -44,6 +44,32 @@ cudaEvent_t get_event(fc_ctx* c, size_t i) {
     return c->events[i];
 }
 
+// Tile interleave of the multi-GPU renders: the XY root tiles (tx, ty) of the band with
+// (tx + ty) % stride == offset, in row-major order, as ids (ty - row0) * roots_x + tx.
+static void owned_tiles(uint32_t roots_x, uint32_t row0, uint32_t row1, uint32_t stride, uint32_t offset,
+                        std::vector<uint32_t>& ids) {
+    ids.clear();
+    for (uint32_t ty = row0; ty < row1; ++ty)
+        for (uint32_t tx = 0; tx < roots_x; ++tx)
+            if ((tx + ty) % stride == offset) ids.push_back((ty - row0) * roots_x + tx);
+}
+int32_t root_subset(fc_ctx* c, uint32_t roots_x, uint32_t row0, uint32_t row1, uint32_t stride, uint32_t offset,
+                    cudaStream_t s, const uint32_t** d_list, uint32_t* n) {
+    const uint32_t key[5] = {roots_x, row0, row1, stride, offset};
+    if (memcmp(key, c->root_list_key, sizeof key) != 0 || !c->root_list.p) {
+        std::vector<uint32_t> ids;
+        owned_tiles(roots_x, row0, row1, stride, offset, ids);
+        CU(cudaStreamSynchronize(s));   // a previous launch may still read the old list
+        CU(c->root_list.ensure(std::max<size_t>(ids.size(), 1) * 4));
+        if (!ids.empty()) CU(cudaMemcpy(c->root_list.p, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice));
+        memcpy(c->root_list_key, key, sizeof key);
+        c->root_list_n = uint32_t(ids.size());
+    }
+    *d_list = c->root_list.as<uint32_t>();
+    *n = c->root_list_n;
+    return FC_OK;
+}
+
 extern "C" {
 
 int32_t fc_render2d(fc_ctx* c, const fc_tape* tape, const fc_render2d_cfg* cfg, float* out, fc_render_stats* stats) {
@@ -64,11 +90,18 @@ int32_t fc_render2d(fc_ctx* c, const fc_tape* tape, const fc_render2d_cfg* cfg, 
     uint32_t row0 = cfg->root_row_begin, row1 = cfg->root_row_end ? cfg->root_row_end : roots_y_all;
     if (row0 > row1 || row1 > roots_y_all) return fail(FC_ERR_INVALID, "bad root row band");
     const uint32_t roots_y = row1 - row0;
-    const uint64_t n_roots = uint64_t(roots_x) * roots_y;
     const bool timing = (cfg->flags & FC_FLAG_TIMING) != 0;
     const bool async = (cfg->flags & FC_FLAG_ASYNC) != 0;
     const bool want_stats = stats != nullptr;
     cudaStream_t s = c->stream;
+    const uint32_t* d_roots = nullptr;
+    uint32_t n_list = 0;
+    if (cfg->root_stride > 1) {
+        if (cfg->root_offset >= cfg->root_stride) return fail(FC_ERR_INVALID, "root_offset must be below root_stride");
+        if (!is_device_ptr(out)) return fail(FC_ERR_UNSUPPORTED, "tile-interleaved renders need a device image");
+        if (int32_t lrc = root_subset(c, roots_x, row0, row1, cfg->root_stride, cfg->root_offset, s, &d_roots, &n_list)) return lrc;
+    }
+    const uint64_t n_roots = d_roots ? uint64_t(n_list) : uint64_t(roots_x) * roots_y;
     const bool serial_fill = env_int("FIDGET_B200_SERIAL_FILL", 0) != 0;
 
     // ---- scratch ----
@@ -91,7 +124,15 @@ int32_t fc_render2d(fc_ctx* c, const fc_tape* tape, const fc_render2d_cfg* cfg, 
     bool out_dev = is_device_ptr(out);
     float* dimg = out;
     const size_t img_bytes = size_t(cfg->width) * cfg->height * 4;
-    if (!out_dev) {
+    const uint32_t fmt = cfg->out_format;
+    if (fmt > FC_OUT_RGBA8) return fail(FC_ERR_INVALID, "unknown out_format");
+    if (fmt != FC_OUT_F32) {
+        // the distance image lives in the context; `out` receives the derived format at the end
+        if (cfg->root_stride > 1 || cfg->root_row_begin || cfg->root_row_end)
+            return fail(FC_ERR_UNSUPPORTED, "out_format other than FC_OUT_F32 needs a whole-frame render");
+        CU(c->image.ensure(img_bytes));
+        dimg = c->image.as<float>();
+    } else if (!out_dev) {
         void* alias = env_int("FIDGET_B200_ZEROCOPY", 0) ? pinned_device_alias(out) : nullptr;
         if (alias) {
             dimg = static_cast<float*>(alias);   // zero-copy: kernels store straight into the host image
@@ -120,6 +161,7 @@ int32_t fc_render2d(fc_ctx* c, const fc_tape* tape, const fc_render2d_cfg* cfg, 
         p.root_mode = (l == 0);
         p.roots_x = roots_x; p.roots_y = roots_y; p.roots_z = 1;
         p.root_x0 = 0; p.root_y0 = row0 * T0; p.root_z0 = 0;
+        p.root_list = d_roots; p.n_root_list = n_list;
         p.root_tape.ptr = tape->dev;
         p.root_tape.n_ops = tape->info.n_ops;
         p.root_tape.ref_len = tape->info.ref_len;
@@ -198,7 +240,20 @@ int32_t fc_render2d(fc_ctx* c, const fc_tape* tape, const fc_render2d_cfg* cfg, 
     }
     if (timing) CU(cudaEventRecord(get_event(c, ev++), s));
     CU(cudaGetLastError());
-    if (!out_dev) {   // only the rows of the requested band are copied back
+    if (fmt != FC_OUT_F32) {
+        const size_t fb = fmt == FC_OUT_MASK_U8 ? size_t(cfg->width) * cfg->height
+                        : fmt == FC_OUT_BITMAP_1BIT ? size_t((cfg->width + 7) / 8) * cfg->height : img_bytes;
+        uint8_t* dfmt = reinterpret_cast<uint8_t*>(out);
+        if (!out_dev) {
+            CU(c->fx_out.ensure(fb));
+            dfmt = c->fx_out.as<uint8_t>();
+        }
+        if (fmt == FC_OUT_RGBA8) launch_to_rgba(0, dimg, uint64_t(cfg->width) * cfg->height, dfmt, s);
+        else launch_to_mask(dimg, cfg->width, cfg->height, dfmt, fmt == FC_OUT_BITMAP_1BIT, s);
+        ++launches;
+        CU(cudaGetLastError());
+        if (!out_dev) CU(cudaMemcpyAsync(out, dfmt, fb, cudaMemcpyDeviceToHost, s));
+    } else if (!out_dev) {   // only the rows of the requested band are copied back
         const uint32_t by0 = std::min(row0 * T0, cfg->height), by1 = std::min(row1 * T0, cfg->height);
         if (by1 > by0)
             CU(cudaMemcpyAsync(out + size_t(by0) * cfg->width, dimg + size_t(by0) * cfg->width,
@@ -263,12 +318,20 @@ int32_t fc_render3d(fc_ctx* c, const fc_tape* tape, const fc_render3d_cfg* cfg, 
     if (z_begin % T0 || z_begin >= z_end || z_end > ((cfg->depth + T0 - 1) / T0) * T0)
         return fail(FC_ERR_INVALID, "z slab must start on a root-tile boundary inside the volume");
     const uint32_t roots_z = (std::min(z_end, ((cfg->depth + T0 - 1) / T0) * T0) - z_begin + T0 - 1) / T0;
-    const uint64_t n_roots = uint64_t(roots_x) * roots_y * roots_z;
-    if (n_roots > 0xfffffff0ull) return fail(FC_ERR_UNSUPPORTED, "volume too large");
     const bool timing = (cfg->flags & FC_FLAG_TIMING) != 0;
     const bool async = (cfg->flags & FC_FLAG_ASYNC) != 0;
     const bool want_stats = stats != nullptr;
     cudaStream_t s = c->stream;
+    const uint32_t* d_roots = nullptr;
+    uint32_t n_list = 0;
+    if (cfg->root_stride > 1) {
+        if (cfg->root_offset >= cfg->root_stride) return fail(FC_ERR_INVALID, "root_offset must be below root_stride");
+        if (!is_device_ptr(out)) return fail(FC_ERR_UNSUPPORTED, "tile-interleaved renders need a device image");
+        if (T0 % 8) return fail(FC_ERR_UNSUPPORTED, "tile-interleaved renders need a root tile edge that is a multiple of 8");
+        if (int32_t lrc = root_subset(c, roots_x, row0, row1, cfg->root_stride, cfg->root_offset, s, &d_roots, &n_list)) return lrc;
+    }
+    const uint64_t n_roots = (d_roots ? uint64_t(n_list) : uint64_t(roots_x) * roots_y) * roots_z;
+    if (n_roots > 0xfffffff0ull) return fail(FC_ERR_UNSUPPORTED, "volume too large");
 
     const int bps = env_int("FIDGET_B200_BLOCKS_PER_SM", 6);
     const int grid_blocks = c->sm_count * bps;
@@ -319,6 +382,7 @@ int32_t fc_render3d(fc_ctx* c, const fc_tape* tape, const fc_render3d_cfg* cfg, 
         p.root_mode = (l == 0);
         p.roots_x = roots_x; p.roots_y = roots_y; p.roots_z = roots_z;
         p.root_x0 = 0; p.root_y0 = row0 * T0; p.root_z0 = z_begin;
+        p.root_list = d_roots; p.n_root_list = n_list;
         p.root_tape.ptr = tape->dev;
         p.root_tape.n_ops = tape->info.n_ops;
         p.root_tape.ref_len = tape->info.ref_len;
@@ -385,6 +449,7 @@ int32_t fc_render3d(fc_ctx* c, const fc_tape* tape, const fc_render3d_cfg* cfg, 
         NormalParams q{};
         q.width = cfg->width; q.height = cfg->height; q.depth = cfg->depth;
         q.y0 = band_y0; q.y1 = band_y1;
+        q.root_list = d_roots; q.n_root_list = n_list; q.roots_x = roots_x; q.root_tile = T0;
         q.clamp = (cfg->flags & FC_FLAG_NO_CLAMP) ? 0 : 1;
         memcpy(q.mat.m, cfg->mat, sizeof q.mat.m);
         q.jobs = c->jobs[L].as<TileJob>();
@@ -452,6 +517,54 @@ int32_t fc_merge_slabs(fc_ctx* c, const fc_geometry_pixel* const* slabs, uint32_
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
     return FC_OK;
+}
+
+uint32_t fc_tiles_per_rank(uint32_t width, uint32_t height, uint32_t root_tile, uint32_t n_ranks) {
+    if (!root_tile || !n_ranks) return 0;
+    const uint32_t rx = (width + root_tile - 1) / root_tile, ry = (height + root_tile - 1) / root_tile;
+    uint32_t best = 0;
+    std::vector<uint32_t> ids;
+    for (uint32_t r = 0; r < n_ranks; ++r) {
+        owned_tiles(rx, 0, ry, n_ranks, r, ids);
+        best = std::max(best, uint32_t(ids.size()));
+    }
+    return best;
+}
+
+static int32_t tiles_copy(fc_ctx* c, const void* src, void* dst, uint32_t width, uint32_t height, uint32_t px_bytes,
+                          uint32_t T, uint32_t n_ranks, int rank /* -1: unpack all */) {
+    if (!c || !src || !dst) return fail(FC_ERR_INVALID, "null argument");
+    if (px_bytes != 4 && px_bytes != 16) return fail(FC_ERR_INVALID, "px_bytes must be 4 or 16");
+    if (!T || !n_ranks || (rank >= 0 && uint32_t(rank) >= n_ranks)) return fail(FC_ERR_INVALID, "bad tile interleave");
+    if (!is_device_ptr(src) || !is_device_ptr(dst)) return fail(FC_ERR_INVALID, "fc_tiles_pack/unpack take device pointers");
+    std::lock_guard<std::mutex> guard(c->mu);
+    CU(cudaSetDevice(c->device));
+    const uint32_t rx = (width + T - 1) / T, ry = (height + T - 1) / T;
+    const uint32_t per = fc_tiles_per_rank(width, height, T, n_ranks);
+    // slot of every image tile inside the gathered buffer: owner * per + index in the owner's list
+    const uint32_t key[4] = {rx, ry, n_ranks, T};
+    if (memcmp(key, c->tile_slots_key, sizeof key) != 0 || !c->tile_slots.p) {
+        std::vector<uint32_t> slots(size_t(rx) * ry), ids;
+        for (uint32_t r = 0; r < n_ranks; ++r) {
+            owned_tiles(rx, 0, ry, n_ranks, r, ids);
+            for (size_t k = 0; k < ids.size(); ++k) slots[ids[k]] = r * per + uint32_t(k);
+        }
+        CU(cudaStreamSynchronize(c->stream));
+        CU(c->tile_slots.ensure(slots.size() * 4));
+        CU(cudaMemcpy(c->tile_slots.p, slots.data(), slots.size() * 4, cudaMemcpyHostToDevice));
+        memcpy(c->tile_slots_key, key, sizeof key);
+    }
+    launch_tiles_copy(src, dst, width, height, px_bytes, T, rx, ry, c->tile_slots.as<uint32_t>(), n_ranks, per, rank, c->stream);
+    CU(cudaGetLastError());
+    return FC_OK;
+}
+int32_t fc_tiles_pack(fc_ctx* c, const void* image, uint32_t width, uint32_t height, uint32_t px_bytes, uint32_t root_tile,
+                      uint32_t n_ranks, uint32_t rank, void* packed) {
+    return tiles_copy(c, image, packed, width, height, px_bytes, root_tile, n_ranks, int(rank));
+}
+int32_t fc_tiles_unpack(fc_ctx* c, const void* gathered, uint32_t width, uint32_t height, uint32_t px_bytes, uint32_t root_tile,
+                        uint32_t n_ranks, void* image) {
+    return tiles_copy(c, gathered, image, width, height, px_bytes, root_tile, n_ranks, -1);
 }
 
 }  // extern "C"

@@ -318,6 +318,8 @@ class RenderConfig2D:
     root_rows: tuple = (0, 0)                   # band of root-tile rows (multi-GPU)
     timing: bool = False
     var_values: tuple = ()                      # ShapeVars: value per tape input slot (axis slots ignored)
+    interleave: tuple = (0, 0)                  # (N, r): only root tiles with (tx + ty) % N == r (multi-GPU)
+    out_format: str = "f32"                     # "f32" | "mask_u8" | "bitmap_1bit" | "rgba8"
 
     def matrix(self):
         return self.mat if self.mat is not None else pixel_mat(self.width, self.height, self.world_to_model)
@@ -336,10 +338,15 @@ class RenderConfig3D:
     timing: bool = False
     var_values: tuple = ()
     clamp: bool = True                          # False for slab renders (fc_merge_slabs applies it)
+    interleave: tuple = (0, 0)                  # (N, r): only root-tile columns with (tx + ty) % N == r
 
     def matrix(self):
         return self.mat if self.mat is not None else voxel_mat(self.width, self.height, self.depth,
                                                                self.world_to_model)
+
+
+OUT_FORMATS = {"f32": _lib.FC_OUT_F32, "mask_u8": _lib.FC_OUT_MASK_U8, "bitmap_1bit": _lib.FC_OUT_BITMAP_1BIT,
+               "rgba8": _lib.FC_OUT_RGBA8}
 
 
 def render2d(shape: CudaShape, cfg: RenderConfig2D, out=None, stats: bool = False, asynchronous: bool = False):
@@ -356,11 +363,20 @@ def render2d(shape: CudaShape, cfg: RenderConfig2D, out=None, stats: bool = Fals
         c.tile_sizes[i] = t
     c.flags = (_lib.FC_FLAG_TIMING if cfg.timing else 0) | (_lib.FC_FLAG_ASYNC if asynchronous else 0)
     c.root_row_begin, c.root_row_end = cfg.root_rows
+    c.root_stride, c.root_offset = cfg.interleave
     c.n_var_values = len(cfg.var_values)
     for i, v in enumerate(cfg.var_values):
         c.var_values[i] = float(v)
+    c.out_format = OUT_FORMATS[cfg.out_format]
     if out is None:
-        out = np.zeros((cfg.height, cfg.width), dtype=np.float32)
+        if cfg.out_format == "f32":
+            out = np.zeros((cfg.height, cfg.width), dtype=np.float32)
+        elif cfg.out_format == "mask_u8":
+            out = np.zeros((cfg.height, cfg.width), dtype=np.uint8)
+        elif cfg.out_format == "bitmap_1bit":
+            out = np.zeros((cfg.height, (cfg.width + 7) // 8), dtype=np.uint8)
+        else:
+            out = np.zeros((cfg.height, cfg.width, 4), dtype=np.uint8)
     st = _lib.FcRenderStats() if stats else None
     _ck(lib.fc_render2d(shape.cuda._h, shape._h, C.byref(c), _ptr(out), C.byref(st) if stats else None))
     return (out, st.as_dict()) if stats else out
@@ -379,6 +395,7 @@ def render3d(shape: CudaShape, cfg: RenderConfig3D, out=None, stats: bool = Fals
         (0 if cfg.clamp else _lib.FC_FLAG_NO_CLAMP)
     c.z_begin, c.z_end = cfg.z_range
     c.root_row_begin, c.root_row_end = cfg.root_rows
+    c.root_stride, c.root_offset = cfg.interleave
     c.n_var_values = len(cfg.var_values)
     for i, v in enumerate(cfg.var_values):
         c.var_values[i] = float(v)

@@ -45,7 +45,7 @@ typedef struct fc_eval fc_eval;  /* per-thread evaluator scratch */
 
 const char* fc_last_error(void);
 /* Library/ABI version; bumped on any signature change */
-uint32_t fc_abi_version(void);
+uint32_t fc_abi_version(void);   /* 2: root_stride/root_offset, fc_tiles_* */
 
 /* ---- lifecycle ---------------------------------------------------------- */
 int32_t fc_ctx_create(int32_t device, fc_ctx** out);
@@ -137,6 +137,10 @@ int32_t fc_simplify(fc_eval* e, const fc_tape* parent, const uint8_t* choices, s
 #define FC_FLAG_TIMING 2u       /* record per-stage CUDA events (fc_render_stats.stage_ms) */
 #define FC_FLAG_NO_CLAMP 4u     /* fc_render3d: skip the final depth clamp (slab renders; fc_merge_slabs applies it) */
 
+#define FC_OUT_F32 0u          /* width*height RawDistancePixel bits as f32 (pixel::render's own output) */
+#define FC_OUT_MASK_U8 1u      /* width*height bytes: 255 inside, 0 outside */
+#define FC_OUT_BITMAP_1BIT 2u  /* height rows of (width+7)/8 bytes; bit x%8 (LSB first) of byte x/8 set = inside */
+#define FC_OUT_RGBA8 3u        /* width*height*4 bytes: effects::to_rgba_bitmap(image, false) */
 typedef struct fc_render2d_cfg {
     uint32_t width, height;
     float mat[16];              /* row-major 4x4, screen -> model: RenderConfig::mat() embedded as in
@@ -153,6 +157,15 @@ typedef struct fc_render2d_cfg {
      * (entries at axis slots are ignored); n_var_values may be 0 for plain X/Y/Z shapes. */
     uint32_t n_var_values;
     float var_values[FC_MAX_VARS];
+    /* Multi-GPU tile interleave: with root_stride = N > 1 only the root tiles (tx, ty) with
+     * (tx + ty) % N == root_offset are rendered (the analogue of rayon handing root tiles to worker
+     * threads, fidget-raster/src/lib.rs:152-165); other pixels are left untouched, and `out` must be a
+     * device image.  0 or 1 = every root tile. */
+    uint32_t root_stride, root_offset;
+    /* What `out` receives (FC_OUT_*).  The distance image is always produced in HBM; the smaller formats
+     * are derived from it on the device (RawDistancePixel::inside, pixel.rs:177-183 / effects::to_rgba_bitmap,
+     * effects.rs:446-466), so a host caller pays the PCIe copy of the small image only. */
+    uint32_t out_format;
 } fc_render2d_cfg;
 
 typedef struct fc_geometry_pixel { float normal[3]; uint32_t depth; } fc_geometry_pixel; /* voxel.rs:126-134 */
@@ -172,6 +185,7 @@ typedef struct fc_render3d_cfg {
      * balances surface-like work better than Z slabs); row_end = 0 means all rows.  Only the rows
      * of the band are written. */
     uint32_t root_row_begin, root_row_end;
+    uint32_t root_stride, root_offset;   /* tile interleave, as in fc_render2d_cfg (full depth per tile column) */
 } fc_render3d_cfg;
 
 typedef struct fc_render_stats {
@@ -201,6 +215,18 @@ int32_t fc_render3d(fc_ctx* ctx, const fc_tape* tape, const fc_render3d_cfg* cfg
  * voxel.rs:535-546.  Used after the all-gather in multi-GPU renders. */
 int32_t fc_merge_slabs(fc_ctx* ctx, const fc_geometry_pixel* const* slabs, uint32_t n_slabs,
                        uint32_t width, uint32_t height, uint32_t depth, fc_geometry_pixel* out);
+
+/* Tile-interleaved sharding (root_stride / root_offset above): the root tiles of rank r, in row-major
+ * order, packed as [tile][root_tile rows][root_tile pixels] -- the contiguous chunk an all-gather needs.
+ * Every rank's chunk holds fc_tiles_per_rank() tiles (ranks owning fewer leave the tail unused).
+ * px_bytes is 4 (fc_render2d images) or 16 (fc_render3d images).  Device pointers; the calls only
+ * ENQUEUE on the context's stream. */
+uint32_t fc_tiles_per_rank(uint32_t width, uint32_t height, uint32_t root_tile, uint32_t n_ranks);
+int32_t fc_tiles_pack(fc_ctx* ctx, const void* image, uint32_t width, uint32_t height, uint32_t px_bytes,
+                      uint32_t root_tile, uint32_t n_ranks, uint32_t rank, void* packed);
+/* gathered: n_ranks chunks in rank order (the output of the all-gather); writes every pixel of `image`. */
+int32_t fc_tiles_unpack(fc_ctx* ctx, const void* gathered, uint32_t width, uint32_t height, uint32_t px_bytes,
+                        uint32_t root_tile, uint32_t n_ranks, void* image);
 
 /* ---- octree sampler (fidget-mesh) ----------------------------------------- */
 /* The sampling half of Octree::build (fidget-mesh/src/octree.rs:521-808): interval

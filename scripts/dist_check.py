@@ -1,40 +1,78 @@
-"""torchrun script: sharded renders (2D bands, 3D Z slabs) must equal the single-GPU result byte for byte."""
+"""torchrun script (NCCL, N GPUs): the sharded renders of fidget_b200.shard must reproduce the single-GPU images
+byte for byte on every rank.  Prints one line per check on rank 0; exits non-zero on a mismatch.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 scripts/dist_check.py
+"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch, torch.distributed as dist
+import torch, torch.distributed as dist
 import fidget_b200 as fb
-from fidget_b200.shard import render2d_bands, render3d_zslabs
+from fidget_b200 import shard
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-cuda = fb.CudaContext(local)
-cuda.set_stream(torch.cuda.current_stream().cuda_stream)
-root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-shape = fb.CudaShape.from_vm(cuda, open(os.path.join(root, "models", "prospero.vm")).read())
 dev = torch.device("cuda", local)
+cuda = fb.CudaContext(local)
+cuda.set_arena_bytes(4 << 30)
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ok = True
-# 2D
+
+
+def check(name, a, b):
+    global ok
+    same = torch.equal(a.view(torch.int32), b.view(torch.int32))
+    t = torch.tensor([int(same)], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"{name}: {'identical on all ranks' if int(t) else 'MISMATCH'}", flush=True)
+    ok = ok and bool(int(t))
+
+
+def model(name):
+    return fb.CudaShape.from_vm(cuda, open(os.path.join(root, "models", name)).read())
+
+
+# 2D: interleaved tiles and bands
+s = model("prospero.vm")
 n = 2048
-img = torch.zeros((n, n), dtype=torch.float32, device=dev)
-gat = torch.empty_like(img)
-render2d_bands(shape, fb.RenderConfig2D(n, n), img, gat)
-torch.cuda.synchronize()
+cfg = fb.RenderConfig2D(n, n)
 full = torch.zeros((n, n), dtype=torch.float32, device=dev)
-fb.render2d(shape, fb.RenderConfig2D(n, n), out=full)
-same2d = bool(torch.equal(gat.view(torch.int32), full.view(torch.int32)))
-# 3D
-col = fb.CudaShape.from_vm(cuda, open(os.path.join(root, "models", "colonnade.vm")).read())
-m = 512
-slab = torch.zeros((m, m, 4), dtype=torch.float32, device=dev)
-g3 = torch.empty((world, m, m, 4), dtype=torch.float32, device=dev)
-out3 = torch.zeros((m, m, 4), dtype=torch.float32, device=dev)
-render3d_zslabs(col, fb.RenderConfig3D(m, m, m), slab, g3, out3)
+fb.render2d(s, cfg, out=full)
+img = torch.zeros_like(full)
+chunk, gathered = shard.tile_buffers(world, n, n, 1, dev)
+shard.render2d_tiles(s, cfg, img, chunk, gathered)
 torch.cuda.synchronize()
-full3 = torch.zeros((m, m, 4), dtype=torch.float32, device=dev)
-fb.render3d(col, fb.RenderConfig3D(m, m, m), out=full3)
-same3d = bool(torch.equal(out3.view(torch.int32), full3.view(torch.int32)))
-print(f"rank {rank}/{world}: 2D bands identical={same2d}  3D slabs identical={same3d}", flush=True)
+check(f"2D prospero {n}^2, {world} ranks, interleaved tiles + 1 all-gather", img, full)
+if (n // 128) % world == 0:
+    g2 = torch.zeros_like(full)
+    shard.render2d_bands(s, cfg, img, g2)
+    torch.cuda.synchronize()
+    check(f"2D prospero {n}^2, {world} ranks, row bands + 1 all-gather", g2, full)
+
+# 3D: interleaved tiles, Y bands, Z slabs
+for name, n in (("bear.vm", 512), ("prospero.vm", 1024)):
+    s = model(name)
+    cfg = fb.RenderConfig3D(n, n, n)
+    full = torch.zeros((n, n, 4), dtype=torch.float32, device=dev)
+    fb.render3d(s, cfg, out=full)
+    img = torch.zeros_like(full)
+    chunk, gathered = shard.tile_buffers(world, n, n, 4, dev)
+    shard.render3d_tiles(s, cfg, img, chunk, gathered)
+    torch.cuda.synchronize()
+    check(f"3D {name} {n}^3, {world} ranks, interleaved tile columns + 1 all-gather", img, full)
+    if (n // 128) % world == 0:
+        g2 = torch.zeros_like(full)
+        shard.render3d_ybands(s, cfg, img, g2)
+        torch.cuda.synchronize()
+        check(f"3D {name} {n}^3, {world} ranks, Y bands + 1 all-gather", g2, full)
+        slab = torch.zeros_like(full)
+        gs = torch.zeros((world, n, n, 4), dtype=torch.float32, device=dev)
+        out = torch.zeros_like(full)
+        shard.render3d_zslabs(s, cfg, slab, gs, out)
+        torch.cuda.synchronize()
+        check(f"3D {name} {n}^3, {world} ranks, Z slabs + 1 all-gather + merge", out, full)
+cuda.synchronize()
 dist.barrier()
 dist.destroy_process_group()
-sys.exit(0 if (same2d and same3d) else 1)
+sys.exit(0 if ok else 1)

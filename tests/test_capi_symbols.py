@@ -25,14 +25,14 @@ def test_library_exports_every_declared_symbol():
     assert not missing, missing
     # the Python binding table covers the whole CUDA header too
     assert sorted(_lib.CUDA_API) == declared("include/fidget_cuda.h", "fc_")
-    assert lib.fc_abi_version() == 1
+    assert lib.fc_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
     from fidget_b200 import _lib
     assert C.sizeof(_lib.FcTapeInfo) == 7 * 4
-    assert C.sizeof(_lib.FcRender2dCfg) == 4 * 2 + 64 + 4 + 4 + 4 + 32 + 4 + 8 + 4 + 64
-    assert C.sizeof(_lib.FcRender3dCfg) == 4 * 3 + 64 + 4 + 32 + 4 + 8 + 4 + 64 + 8
+    assert C.sizeof(_lib.FcRender2dCfg) == 4 * 2 + 64 + 4 + 4 + 4 + 32 + 4 + 8 + 4 + 64 + 8 + 4
+    assert C.sizeof(_lib.FcRender3dCfg) == 4 * 3 + 64 + 4 + 32 + 4 + 8 + 4 + 64 + 8 + 8
     assert C.sizeof(_lib.FcRenderStats) == 5 * 64 + 3 * 8 + 4 + 16 * 4 + 4  # + tail padding to 8
 
 

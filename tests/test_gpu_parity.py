@@ -249,6 +249,48 @@ def test_render3d_ybands_assemble_to_full_image(cuda):
         fb.render3d(shape, fb.RenderConfig3D(n, n, n, root_rows=(3, 9)))
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_tile_interleave_assembles_to_full_image(cuda, world):
+    """The sharding bench.py measures at N > 1, on one GPU: every "rank" renders its interleaved root tiles,
+    packs its chunk (fc_tiles_pack); the concatenated chunks (what the all-gather delivers) are unpacked
+    (fc_tiles_unpack) into the very bytes of a plain full render -- 2D and 3D, ragged sizes included."""
+    import ctypes as C
+    import torch
+    from fidget_b200 import _lib
+    from fidget_b200.shard import tiles_per_rank
+    lib = _lib.load()
+    for dim, name, dims in ((2, "prospero.vm", (1000, 600)), (2, "hi.vm", (512, 512)), (3, "colonnade.vm", (300, 260, 256)),
+                            (3, "bear.vm", (512, 512, 512))):
+        shape = fb.CudaShape.from_vm(cuda, model_text(name))
+        w, h = dims[0], dims[1]
+        px = 1 if dim == 2 else 4
+        if dim == 2:
+            full = torch.zeros((h, w), dtype=torch.float32, device="cuda")
+            fb.render2d(shape, fb.RenderConfig2D(w, h), out=full)
+        else:
+            full = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+            fb.render3d(shape, fb.RenderConfig3D(w, h, dims[2]), out=full)
+        per = tiles_per_rank(world, w, h)
+        gathered = torch.zeros((world * per, 128, 128, px), dtype=torch.float32, device="cuda")
+        for r in range(world):
+            img = torch.full_like(full, 7.0)
+            if dim == 2:
+                fb.render2d(shape, fb.RenderConfig2D(w, h, interleave=(world, r)), out=img)
+            else:
+                fb.render3d(shape, fb.RenderConfig3D(w, h, dims[2], interleave=(world, r)), out=img)
+            assert lib.fc_tiles_pack(cuda._h, C.c_void_p(img.data_ptr()), w, h, 4 * px, 128, world, r,
+                                     C.c_void_p(gathered[r * per:].data_ptr())) == 0
+        out = torch.full_like(full, 9.0)
+        assert lib.fc_tiles_unpack(cuda._h, C.c_void_p(gathered.data_ptr()), w, h, 4 * px, 128, world,
+                                   C.c_void_p(out.data_ptr())) == 0
+        cuda.synchronize()
+        assert torch.equal(out.view(torch.int32), full.view(torch.int32)), (dim, name, world)
+    with pytest.raises(fb.CudaError):      # a host image cannot take an interleaved render
+        fb.render2d(shape, fb.RenderConfig2D(256, 256, interleave=(2, 0)))
+    with pytest.raises(fb.CudaError):
+        fb.render2d(shape, fb.RenderConfig2D(256, 256, interleave=(2, 2)), out=torch.zeros((256, 256), device="cuda"))
+
+
 def test_golden_hi_variants(cuda):
     gs = fb.CudaShape.from_vm(cuda, model_text("hi.vm"))
     assert _rows(fb.render2d(gs, fb.RenderConfig2D(32, 32))) == _PIX["check_hi:EXPECTED"]["rows"]
@@ -565,3 +607,68 @@ def test_c_client_renders_like_the_python_face(cuda, tmp_path):
             h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
         assert f"inside {int(fb.pixel_inside(img).sum())} px" in out, out
         assert f"fnv1a {h:016x}" in out, out
+
+
+@pytest.mark.parametrize("n", [4096, 4097, 5119, 8192, 100003])
+def test_slice_tma_path_matches_per_thread_path_and_oracle(orc, cuda, monkeypatch, n):
+    """fc_float_slice_eval / fc_grad_slice_eval take the TMA-fed persistent kernel (bulk.cu) for n >= 4096 on
+    tapes without spills: same bits as the per-thread kernel (FIDGET_B200_NO_TMA=1) and as the oracle, full
+    tiles and ragged tails, host and device slices."""
+    import torch
+    for name, exact in (("hi.vm", True), ("colonnade.vm", True), ("bear.vm", False)):
+        ot, gs = _pair(orc, cuda, name)
+        pts = _points(n, ot.n_vars, n)
+        want = ot.float_slice_eval(pts)
+        monkeypatch.setenv("FIDGET_B200_NO_TMA", "0")
+        fast = np.asarray(gs.float_slice_eval(pts))
+        dev_pts = [torch.from_numpy(p).cuda() for p in pts]
+        fast_dev = gs.float_slice_eval(dev_pts).cpu().numpy()
+        monkeypatch.setenv("FIDGET_B200_NO_TMA", "1")
+        slow = np.asarray(gs.float_slice_eval(pts))
+        assert same_f32(fast, slow) and same_f32(fast_dev, slow), name
+        if exact:
+            assert same_f32(fast, want), name
+        else:
+            assert np.allclose(fast, want, rtol=1e-5, atol=1e-5, equal_nan=True)
+        # gradients
+        rng = np.random.default_rng(n)
+        vars_ = []
+        for k in range(ot.n_vars):
+            g = np.zeros((n, 4), dtype=np.float32)
+            g[:, 0] = pts[k]
+            g[:, 1 + (k % 3)] = 1.0
+            g[:, 1:] += rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+            vars_.append(g)
+        gwant = ot.grad_slice_eval(vars_)
+        gslow = np.asarray(gs.grad_slice_eval(vars_))
+        monkeypatch.setenv("FIDGET_B200_NO_TMA", "0")
+        gfast = np.asarray(gs.grad_slice_eval(vars_))
+        assert same_f32(gfast, gslow), name
+        if exact:
+            assert same_f32(gfast, gwant), name
+        else:
+            assert np.allclose(gfast, gwant, rtol=1e-5, atol=1e-5, equal_nan=True)
+
+
+@pytest.mark.parametrize("w,h", [(256, 256), (1000, 37), (33, 65), (4096, 4096)])
+def test_render2d_output_formats(orc, cuda, w, h):
+    """fc_render2d_cfg.out_format: the byte mask, the 1-bit bitmap and the RGBA8 bitmap are exactly
+    RawDistancePixel::inside / effects::to_rgba_bitmap of the distance image -- host and device outputs."""
+    import torch
+    name = "prospero.vm" if w == 4096 else "hi.vm"
+    ot, gs = _pair(orc, cuda, name)
+    o_img, _ = orc.render2d(ot, w, h, threads=8)
+    inside = orc.pixel_inside(o_img)
+    f32 = fb.render2d(gs, fb.RenderConfig2D(w, h))
+    assert np.array_equal(f32.view(np.uint32), o_img.view(np.uint32))
+    mask = fb.render2d(gs, fb.RenderConfig2D(w, h, out_format="mask_u8"))
+    assert np.array_equal(mask, np.where(inside, 255, 0).astype(np.uint8))
+    bits = fb.render2d(gs, fb.RenderConfig2D(w, h, out_format="bitmap_1bit"))
+    assert np.array_equal(bits, np.packbits(inside, axis=1, bitorder="little"))
+    rgba = fb.render2d(gs, fb.RenderConfig2D(w, h, out_format="rgba8"))
+    assert np.array_equal(rgba, orc.to_rgba_bitmap(o_img))
+    dev = torch.zeros((h, (w + 7) // 8), dtype=torch.uint8, device="cuda")
+    fb.render2d(gs, fb.RenderConfig2D(w, h, out_format="bitmap_1bit"), out=dev)
+    assert np.array_equal(dev.cpu().numpy(), bits)
+    with pytest.raises(fb.CudaError):
+        fb.render2d(gs, fb.RenderConfig2D(w, h, out_format="mask_u8", root_rows=(0, 1)))
