@@ -111,6 +111,8 @@ CUDA_API = {
     "fc_tape_get_info": (_i32, [_vp, _P(FcTapeInfo)]),
     "fc_tape_set_axes": (_i32, [_vp, _i32, _i32, _i32]),
     "fc_tape_read": (_i32, [_vp, _P(_u32), C.c_size_t, _P(C.c_size_t)]),
+    "fc_tape_serialize": (_i32, [_vp, _vp, C.c_size_t, _P(C.c_size_t)]),
+    "fc_tape_deserialize": (_i32, [_vp, _vp, C.c_size_t, _P(_vp)]),
     "fc_eval_create": (_i32, [_vp, _P(_vp)]),
     "fc_eval_destroy": (None, [_vp]),
     "fc_interval_eval": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),

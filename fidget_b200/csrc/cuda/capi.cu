@@ -278,6 +278,47 @@ int32_t fc_tape_read(const fc_tape* t, uint32_t* words, size_t cap, size_t* n_wo
     return FC_OK;
 }
 
+int32_t fc_tape_serialize(const fc_tape* t, uint8_t* buf, size_t cap, size_t* n_bytes) {
+    if (!t) return fail(FC_ERR_INVALID, "null tape");
+    std::vector<uint32_t> w;
+    to_bytecode(t->host, w);
+    const size_t need = 4 + 6 * 4 + 3 * 4 + 8 + w.size() * 4;
+    if (n_bytes) *n_bytes = need;
+    if (!buf) return FC_OK;
+    if (cap < need) return fail(FC_ERR_INVALID, "buffer too small");
+    uint8_t* q = buf;
+    auto put32 = [&](uint32_t v) { memcpy(q, &v, 4); q += 4; };
+    memcpy(q, "FTAP", 4); q += 4;
+    put32(1); put32(t->info.reg_count); put32(t->info.mem_count); put32(t->info.n_vars); put32(t->info.n_outputs);
+    put32(t->info.choice_count);
+    for (int k = 0; k < 3; ++k) put32(uint32_t(t->ax[k]));
+    const uint64_t nw = w.size();
+    memcpy(q, &nw, 8); q += 8;
+    memcpy(q, w.data(), nw * 4);
+    return FC_OK;
+}
+int32_t fc_tape_deserialize(fc_ctx* c, const uint8_t* buf, size_t n_bytes, fc_tape** out) {
+    if (!c || !buf || !out) return fail(FC_ERR_INVALID, "null argument");
+    const size_t hdr = 4 + 6 * 4 + 3 * 4 + 8;
+    if (n_bytes < hdr || memcmp(buf, "FTAP", 4) != 0) return fail(FC_ERR_INVALID, "not a tape blob (bad magic)");
+    uint32_t f[9];
+    memcpy(f, buf + 4, sizeof f);
+    if (f[0] != 1) return fail(FC_ERR_INVALID, "unsupported tape blob version " + std::to_string(f[0]));
+    uint64_t nw;
+    memcpy(&nw, buf + 4 + 9 * 4, 8);
+    if (nw > (n_bytes - hdr) / 4) return fail(FC_ERR_INVALID, "truncated tape blob");
+    if (f[1] > 255) return fail(FC_ERR_INVALID, "bad register count");
+    std::vector<uint32_t> words(nw);
+    memcpy(words.data(), buf + hdr, nw * 4);
+    fc_tape* t = nullptr;
+    int32_t rc = fc_tape_create(c, words.data(), words.size(), uint8_t(f[1]), f[2], f[3], f[4], f[5], &t);
+    if (rc) return rc;
+    rc = fc_tape_set_axes(t, int32_t(f[6]), int32_t(f[7]), int32_t(f[8]));
+    if (rc) { fc_tape_release(t); return rc; }
+    *out = t;
+    return FC_OK;
+}
+
 ////////////////////////////////////////////////////////////////////////////
 int32_t fc_eval_create(fc_ctx* c, fc_eval** out) {
     if (!c || !out) return fail(FC_ERR_INVALID, "null argument");

@@ -122,6 +122,28 @@ int32_t fh_tape_bytecode(const fh_tape* t, int32_t repack, uint32_t* words, size
     });
 }
 
+int32_t fh_tape_serialize(const fh_tape* t, uint8_t* buf, size_t cap, size_t* n_bytes) {
+    FH_TRY({
+        Bytecode bc = make_bytecode(t->d.asm_, t->d.n_regs, true);
+        fh_tape_info info;
+        if (fh_tape_get_info(t, &info)) throw std::runtime_error("tape info");
+        const size_t need = 4 + 6 * 4 + 3 * 4 + 8 + bc.words.size() * 4;
+        if (n_bytes) *n_bytes = need;
+        if (buf) {
+            if (cap < need) throw std::runtime_error("serialize: buffer too small");
+            uint8_t* q = buf;
+            auto put32 = [&](uint32_t v) { memcpy(q, &v, 4); q += 4; };
+            memcpy(q, "FTAP", 4); q += 4;
+            put32(1); put32(bc.reg_count); put32(bc.mem_count); put32(info.n_vars); put32(info.output_count);
+            put32(info.choice_count);
+            put32(uint32_t(info.var_x)); put32(uint32_t(info.var_y)); put32(uint32_t(info.var_z));
+            const uint64_t nw = bc.words.size();
+            memcpy(q, &nw, 8); q += 8;
+            memcpy(q, bc.words.data(), nw * 4);
+        }
+    });
+}
+
 size_t fh_tape_dump(const fh_tape* t, int32_t ssa, char* buf, size_t cap) {
     std::string s;
     if (ssa) {

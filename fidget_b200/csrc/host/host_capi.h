@@ -49,6 +49,12 @@ int32_t fh_tape_var(const fh_tape* t, uint32_t i, int32_t* kind, uint64_t* id);
 // query the word count.
 int32_t fh_tape_bytecode(const fh_tape* t, int32_t repack, uint32_t* words, size_t cap,
                          size_t* n_words, uint8_t* reg_count, uint32_t* mem_count);
+// Wire / on-disk form of a tape (the counterpart of serde on VmData, fidget-core/src/vm/data.rs:64): a
+// little-endian blob that carries exactly what fc_tape_create needs.
+//   "FTAP" | version u32 = 1 | reg_count u32 | mem_count u32 | n_vars u32 | n_outputs u32 | choice_count u32
+//   | axis slots i32[3] (X, Y, Z; -1 = unused) | n_words u64 | bytecode words u32[n_words]
+// Call with buf = NULL to query the size.
+int32_t fh_tape_serialize(const fh_tape* t, uint8_t* buf, size_t cap, size_t* n_bytes);
 // Human-readable dump of the register tape in evaluation order (or the SSA
 // tape root-first when ssa != 0); returns bytes needed incl. NUL.
 size_t fh_tape_dump(const fh_tape* t, int32_t ssa, char* buf, size_t cap);

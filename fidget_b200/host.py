@@ -56,6 +56,8 @@ def bind_host_api(lib: C.CDLL) -> C.CDLL:
     lib.fh_tape_get_info.argtypes = [vp, P(FhTapeInfo)]
     lib.fh_tape_var.argtypes = [vp, u32, P(i32), P(C.c_uint64)]
     lib.fh_tape_bytecode.argtypes = [vp, i32, P(u32), C.c_size_t, P(C.c_size_t), P(C.c_uint8), P(u32)]
+    lib.fh_tape_serialize.argtypes = [vp, vp, C.c_size_t, P(C.c_size_t)]
+    lib.fh_tape_serialize.restype = i32
     lib.fh_tape_dump.argtypes = [vp, i32, C.c_char_p, C.c_size_t]
     lib.fh_tape_dump.restype = C.c_size_t
     for name in ("fh_context_new", "fh_context_from_text", "fh_constant", "fh_var", "fh_unary",
@@ -219,6 +221,14 @@ class TapeData:
             self._h, int(repack), words.ctypes.data_as(C.POINTER(C.c_uint32)), n.value,
             C.byref(n), C.byref(rc), C.byref(mc)))
         return Bytecode(words, rc.value, mc.value)
+
+    def serialize(self) -> bytes:
+        """The tape's wire / on-disk blob ("FTAP", see include/fidget_cuda.h): what ``CudaShape.from_blob`` loads."""
+        n = C.c_size_t()
+        _check(self._lib, self._lib.fh_tape_serialize(self._h, None, 0, C.byref(n)))
+        buf = (C.c_uint8 * n.value)()
+        _check(self._lib, self._lib.fh_tape_serialize(self._h, buf, n.value, C.byref(n)))
+        return bytes(buf)
 
     def dump(self, ssa: bool = False) -> str:
         n = self._lib.fh_tape_dump(self._h, int(ssa), None, 0)

@@ -136,6 +136,22 @@ class CudaShape:
         ctx, root = Context.from_text(text)
         return cls(cuda, ctx.tape(root, n_regs))
 
+    @classmethod
+    def from_blob(cls, cuda: CudaContext, blob: bytes):
+        """Loads a serialized tape (``TapeData.serialize`` / ``CudaShape.serialize``): fc_tape_deserialize."""
+        h = C.c_void_p()
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        _ck(cuda._lib.fc_tape_deserialize(cuda._h, buf, len(blob), C.byref(h)))
+        ax = np.frombuffer(blob, dtype=np.int32, count=3, offset=28)
+        return cls(cuda, _handle=h, _axes=tuple(int(a) for a in ax))
+
+    def serialize(self) -> bytes:
+        n = C.c_size_t()
+        _ck(self._lib.fc_tape_serialize(self._h, None, 0, C.byref(n)))
+        buf = (C.c_uint8 * n.value)()
+        _ck(self._lib.fc_tape_serialize(self._h, buf, n.value, C.byref(n)))
+        return bytes(buf)
+
     def __del__(self):
         if getattr(self, "_eval", None):
             self._lib.fc_eval_destroy(self._eval)

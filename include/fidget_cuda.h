@@ -92,6 +92,14 @@ int32_t fc_tape_set_axes(fc_tape* tape, int32_t x, int32_t y, int32_t z);
  * queries the count. */
 int32_t fc_tape_read(const fc_tape* tape, uint32_t* words, size_t cap, size_t* n_words);
 
+/* Wire / on-disk form (the counterpart of serde on VmData, fidget-core/src/vm/data.rs:64):
+ *   "FTAP" | version u32 = 1 | reg_count | mem_count | n_vars | n_outputs | choice_count (u32 each)
+ *   | axis slots i32[3] | n_words u64 | bytecode words u32[n_words]          (little endian)
+ * fc_tape_serialize writes the tape's blob (buf == NULL queries the size); fc_tape_deserialize is
+ * fc_tape_create + fc_tape_set_axes from a blob (as written by fc_tape_serialize or by the host front end). */
+int32_t fc_tape_serialize(const fc_tape* tape, uint8_t* buf, size_t cap, size_t* n_bytes);
+int32_t fc_tape_deserialize(fc_ctx* ctx, const uint8_t* buf, size_t n_bytes, fc_tape** out);
+
 /* ---- trait-level evaluators -------------------------------------------- */
 /* These mirror TracingEvaluator / BulkEvaluator (eval/tracing.rs:26-61,
  * eval/bulk.rs:23-58) the way fidget-jit's raw function pointers do

@@ -262,3 +262,36 @@ def test_ssao_tables_follow_the_reference_construction():
     assert np.allclose(np.linalg.norm(n.astype(np.float64), axis=1), 1.0, rtol=1e-6)
     assert abs(k[:, 0].mean()) < 0.2 and abs(n[:, 0].mean()) < 0.15       # no directional bias
     assert np.array_equal(k, ssao_kernel(64)) and not np.array_equal(k, ssao_kernel(64, seed=1))
+
+
+def test_hand_derived_ssao_and_shading_cases():
+    """Numbers worked out by hand from effects.rs:118-245 (no code in the loop):
+
+    SSAO, 64^3 image, floor at depth 20 with normal (0,0,1), a wall of depth 40 from column 40 on; kernel = one
+    sample (1, 0, 0.5), noise = one rotation (1, 0).  With n = (0,0,1): tangent = (1,0,0), bitangent = (0,1,0),
+    so the sample sits at p + (0.1, 0, 0.05), i.e. 3.2 pixels to the right and 0.05 above the floor.
+      * pixel (37, 32): 37.5 + 3.2 = 40.7 -> column 40, the wall, whose z is 0.625 above the floor: dz = -0.575 < RADIUS
+        and sample.z <= wall z -> occlusion 1 of 1 -> SSAO 0.
+      * pixel (30, 32): lands on the floor, dz = 0.05 < RADIUS but sample.z > floor z -> occlusion 0 -> SSAO 1.
+      * an empty pixel (depth 0) -> NaN.
+    Shading at the image centre (p = 0) with n = (0,0,1): 0.2 + 0.5 * 10/sqrt(150) + 2 * 0.15 * 10/sqrt(125)
+      = 0.2 + 0.408248 + 0.268328 = 0.876576 -> (0.876576 * 255) as u8 = 223; with SSAO 0 the factor 0.4 gives
+      0.350630 * 255 = 89.41 -> 89; with SSAO 1 the factor is 1.0 -> 223 again."""
+    n = 64
+    img = np.zeros((n, n), dtype=GEO)
+    img["depth"] = 20
+    img["depth"][:, 40:] = 40
+    img["normal"] = (0.0, 0.0, 1.0)
+    img["depth"][5, 5] = 0
+    kernel = np.array([[1.0, 0.0, 0.5]], dtype=np.float32)
+    noise = np.array([[1.0, 0.0]], dtype=np.float32)
+    ssao = orc.compute_ssao(img, n, kernel, noise)
+    assert ssao[32, 37] == 0.0
+    assert ssao[32, 30] == 1.0
+    assert np.isnan(ssao[5, 5])
+    flat = np.zeros((n, n), dtype=GEO)
+    flat["depth"] = n // 2
+    flat["normal"] = (0.0, 0.0, 1.0)
+    assert orc.apply_shading(flat, n)[n // 2, n // 2].tolist() == [223, 223, 223]
+    assert orc.apply_shading(flat, n, ssao=np.zeros((n, n), dtype=np.float32))[n // 2, n // 2].tolist() == [89, 89, 89]
+    assert orc.apply_shading(flat, n, ssao=np.ones((n, n), dtype=np.float32))[n // 2, n // 2].tolist() == [223, 223, 223]

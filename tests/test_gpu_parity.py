@@ -672,3 +672,61 @@ def test_render2d_output_formats(orc, cuda, w, h):
     assert np.array_equal(dev.cpu().numpy(), bits)
     with pytest.raises(fb.CudaError):
         fb.render2d(gs, fb.RenderConfig2D(w, h, out_format="mask_u8", root_rows=(0, 1)))
+
+
+def test_tape_blob_round_trip(orc, cuda):
+    """fc_tape_serialize / fc_tape_deserialize (the on-disk / wire form of a tape): a shape loaded from a blob
+    written by the host front end, or by another shape, evaluates and renders identically; damaged blobs fail."""
+    text = model_text("prospero.vm")
+    ctx, root = fb.Context.from_text(text)
+    td = ctx.tape(root)
+    a = fb.CudaShape(cuda, td)
+    blob = td.serialize()
+    assert a.serialize() == blob
+    b = fb.CudaShape.from_blob(cuda, blob)
+    assert (b.size(), b.choice_count, b.n_vars, b._axes) == (a.size(), a.choice_count, a.n_vars, tuple(td.var_slots()))
+    pts = _points(5000, a.n_vars, 3)
+    assert same_f32(a.float_slice_eval(pts), b.float_slice_eval(pts))
+    ia, ib = fb.render2d(a, fb.RenderConfig2D(512, 512)), fb.render2d(b, fb.RenderConfig2D(512, 512))
+    assert np.array_equal(ia.view(np.uint32), ib.view(np.uint32))
+    # a simplified child survives the trip too (alias copies come back as plain copies: same values)
+    box = _boxes(1, a.n_vars, 5, scale=0.1)[0]
+    _, ch, simp = a.interval_eval(box)
+    if simp:
+        child = a.simplify(ch)
+        again = fb.CudaShape.from_blob(cuda, child.serialize())
+        sub = [np.random.default_rng(k).uniform(box[k, 0], box[k, 1], 4100).astype(np.float32) for k in range(a.n_vars)]
+        assert same_f32(child.float_slice_eval(sub), again.float_slice_eval(sub))
+    for bad in (b"", blob[:20], b"XTAP" + blob[4:], blob[:4] + b"\x02\x00\x00\x00" + blob[8:], blob[:-8]):
+        with pytest.raises(fb.CudaError):
+            fb.CudaShape.from_blob(cuda, bad)
+
+
+def test_solver_style_gradient_batches(orc, cuda):
+    """fidget-solver's use of the gradient evaluator (fidget-solver/src/lib.rs:30-36,191): a function of more
+    than three free variables is differentiated three variables at a time over a batch of points -- every
+    partial must match the oracle, and the value column must not depend on which triple carries the seeds."""
+    tapes = []
+    for Ctx in (fb.Context, orc.Context):
+        ctx = Ctx()
+        vs = [ctx.var()[0] for _ in range(5)] + [ctx.x()]
+        e = ctx.sub(ctx.add(ctx.mul(vs[0], vs[1]), ctx.square(ctx.sub(vs[2], vs[5]))), ctx.mul(vs[3], 0.5))
+        e = ctx.max(e, ctx.div(vs[4], ctx.add(ctx.square(vs[0]), 1.0)))
+        tapes.append(ctx.tape(e))
+    g, o = fb.CudaShape(cuda, tapes[0]), orc.Tape.from_data(tapes[1])
+    nv, n = tapes[0].n_vars, 6000
+    rng = np.random.default_rng(12)
+    vals = rng.uniform(-2, 2, (nv, n)).astype(np.float32)
+    values = None
+    for first in range(0, nv, 3):
+        vars_ = []
+        for k in range(nv):
+            a = np.zeros((n, 4), dtype=np.float32)
+            a[:, 0] = vals[k]
+            if first <= k < first + 3:
+                a[:, 1 + k - first] = 1.0
+            vars_.append(a)
+        gg, og = np.asarray(g.grad_slice_eval(vars_)), o.grad_slice_eval(vars_)
+        assert same_f32(gg, og), first
+        values = gg[:, 0] if values is None else values
+        assert same_f32(gg[:, 0], values)

@@ -175,3 +175,21 @@ def test_register_spill_stress_matches_unspilled(orc, Ctx):
     rng = np.random.default_rng(0)
     pts = [rng.uniform(-1, 1, 33).astype(np.float32) for _ in range(3)]
     assert np.array_equal(big.float_slice_eval(pts).view(np.uint32), small.float_slice_eval(pts).view(np.uint32))
+
+
+def test_tape_blob_layout(Ctx):
+    """The wire / on-disk form ("FTAP", include/fidget_cuda.h) carries the bytecode words of
+    fidget_bytecode::Bytecode::new plus exactly the metadata fc_tape_create needs."""
+    import struct
+    ctx, root = Ctx.from_text(model_text("hi.vm"))
+    td = ctx.tape(root)
+    blob, bc = td.serialize(), td.bytecode()
+    assert blob[:4] == b"FTAP"
+    version, regs, mem, n_vars, n_out, n_choice = struct.unpack("<6I", blob[4:28])
+    assert (version, regs, mem, n_vars, n_out, n_choice) == (1, bc.reg_count, bc.mem_count, td.n_vars, 1, td.choice_count)
+    assert struct.unpack("<3i", blob[28:40]) == td.var_slots()
+    (n_words,) = struct.unpack("<Q", blob[40:48])
+    assert n_words == len(bc.words) and len(blob) == 48 + 4 * n_words
+    assert np.array_equal(np.frombuffer(blob, dtype=np.uint32, offset=48), bc.words)
+    spilled = ctx.tape(root, 3)
+    assert struct.unpack("<2I", spilled.serialize()[8:16]) == (3, spilled.bytecode().mem_count)
