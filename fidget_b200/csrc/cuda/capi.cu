@@ -158,6 +158,7 @@ int32_t check_device_errors(fc_ctx* c) {
     CU(cudaMemcpy(&h, c->counters.p, sizeof h, cudaMemcpyDeviceToHost));
     if (h.error & 1u) return fail(FC_ERR_ARENA, "tape arena exhausted during on-device simplification; raise it with fc_ctx_set_arena_bytes");
     if (h.error & 2u) return fail(FC_ERR_CUDA, "internal work list overflow");
+    if (h.error & 4u) return fail(FC_ERR_CUDA, "fused 2D kernel: a queued job never became ready (watchdog)");
     return FC_OK;
 }
 extern "C" {

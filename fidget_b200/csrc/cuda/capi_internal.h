@@ -88,6 +88,7 @@ struct fc_ctx {
     cudaStream_t aux_stream = nullptr;        // fills are painted here, concurrently with the next levels
     cudaEvent_t ev_fork[MAX_LEVELS] = {}, ev_join = nullptr;
     uint64_t arena_bytes = 1ull << 30;
+    uint32_t epoch = 0;                       // ready mark of the current render's job / fill records
     // render scratch
     DevBuf arena, jobs[MAX_LEVELS + 1], fills[MAX_LEVELS], choice_scratch, counters, stats, image, heightmap, leaf_tapes, zsort;
     DevBuf fx_in, fx_out, fx_tmp, fx_tables;  // effects: staged host images, intermediate maps, SSAO tables

@@ -250,6 +250,7 @@ k_interval_root_coop(const __grid_constant__ LevelParams p) {
                     fr.x = cx;
                     fr.y = cy;
                     fr.value = 0x7FC00000u | (fill_in ? 1u : 0u) | (0xF6u << 9);
+                    fr.ready = p.epoch;
                     p.fills[slot] = fr;
                 } else atomicOr(&p.ctr->error, 2u);
             }
@@ -438,9 +439,10 @@ k_interval_root_coop(const __grid_constant__ LevelParams p) {
                 o.x = cx;
                 o.y = cy;
                 o.z = cz;
-                o.pad = 0;
+                o.pad = p.epoch;
                 o.tape = child;
                 p.jobs_out[slot] = o;
+                atomicAdd(&p.ctr->outstanding, 1u);
             } else atomicOr(&p.ctr->error, 2u);
         }
         __syncthreads();

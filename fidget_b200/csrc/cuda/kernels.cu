@@ -22,7 +22,7 @@
 #include <algorithm>
 #include <cstdio>
 
-#include "interp.cuh"
+#include "level_job.cuh"
 
 namespace fdev {
 
@@ -51,173 +51,7 @@ k_interval_level(const __grid_constant__ LevelParams p) {
         j = __shfl_sync(FULL, j, 0);
         if (j >= n_jobs) break;
 
-        TapeRef tr;
-        uint32_t px = 0, py = 0, pz = 0, nchild;
-        if (p.root_mode) {
-            tr = p.root_tape;
-            nchild = min(32u, n_roots - j * 32u);
-        } else {
-            const TileJob* job = p.jobs_in + j;
-            px = job->x;
-            py = job->y;
-            pz = job->z;
-            tr = job->tape;
-            nchild = p.n_axis * p.n_axis * (DIM == 3 ? p.n_axis : 1u);
-        }
-        const uint2* tape = tr.ptr;
-
-        for (uint32_t chunk = 0; chunk * 32u < nchild; ++chunk) {
-            const uint32_t c = chunk * 32u + lane;
-            const bool valid = c < nchild;
-            uint32_t cx, cy, cz = 0;
-            if (p.root_mode) {
-                root_corner(p, j * 32u + (valid ? c : 0u), T, cx, cy, cz);
-            } else {
-                uint32_t cc = valid ? c : 0u;
-                cx = px + (cc % p.n_axis) * T;
-                cy = py + ((cc / p.n_axis) % p.n_axis) * T;
-                if (DIM == 3) cz = pz + (cc / (p.n_axis * p.n_axis)) * T;
-            }
-            // Region in screen coordinates -> model space (pixel.rs:325-342, voxel.rs:291-306)
-            itv X = iv(float(cx), float(cx) + float(T));
-            itv Y = iv(float(cy), float(cy) + float(T));
-            itv Z = DIM == 3 ? iv(float(cz), float(cz) + float(T)) : iv(p.z2d, p.z2d);
-            itv vx, vy, vz;
-            if (DIM == 3 && p.mode == 1u) {
-                // octree cell bounds in world space (CellBounds::child, cell.rs:155-166): dyadic, exact in f32
-                const float h = p.cell_h;
-                X = iv(float(cx) * h - 1.0f, float(cx + T) * h - 1.0f);
-                Y = iv(float(cy) * h - 1.0f, float(cy + T) * h - 1.0f);
-                Z = iv(float(cz) * h - 1.0f, float(cz + T) * h - 1.0f);
-                if (p.has_transform) xform_iv(p.mat, X, Y, Z, vx, vy, vz);
-                else { vx = X; vy = Y; vz = Z; }
-            } else {
-                xform_iv(p.mat, X, Y, Z, vx, vy, vz);
-            }
-
-            ChoicePacker pk;
-            pk.base = cs;
-            itv r = iv_nan();
-            run_interval(
-                tape, tr.n_ops, slots,
-                [&](uint32_t i) { return pick_input(p.vb, i, vx, vy, vz, [](float f) { return iv1(f); }); }, pk,
-                [&](uint32_t oi, itv v) { if (oi == 0) r = v; });
-            pk.finish();
-
-            const bool fill_in = valid && !p.pixel_perfect && r.y < 0.0f;
-            const bool fill_out = valid && !p.pixel_perfect && !fill_in && r.x > 0.0f;
-            const bool amb = valid && !fill_in && !fill_out;
-
-            if (DIM == 3) {
-                // full tile: depth = max(depth, top + 1) over its footprint (voxel.rs:310-317)
-                uint32_t m = p.mode == 1u ? 0u : __ballot_sync(FULL, fill_in);
-                while (m) {
-                    const int src = __ffs(m) - 1;
-                    m &= m - 1;
-                    const uint32_t fx = __shfl_sync(FULL, cx, src), fy = __shfl_sync(FULL, cy, src),
-                                   fz = __shfl_sync(FULL, cz, src);
-                    const unsigned long long key = (unsigned long long)(fz + T + 1u) << 32;
-                    for (uint32_t q = lane; q < T * T; q += 32u) {
-                        const uint32_t x = fx + q % T, y = fy + q / T;
-                        if (x < p.width && y < p.height) atomicMax(&p.heightmap[size_t(y) * p.width + x], key);
-                    }
-                }
-                if (p.stats) {
-                    uint32_t mv = __ballot_sync(FULL, valid), mi = __ballot_sync(FULL, fill_in),
-                             mo = __ballot_sync(FULL, fill_out), ma = __ballot_sync(FULL, amb);
-                    if (lane == 0) {
-                        atomicAdd(&p.stats->evaluated[p.level], (unsigned long long)__popc(mv));
-                        if (mi) atomicAdd(&p.stats->filled_inside[p.level], (unsigned long long)__popc(mi));
-                        if (mo) atomicAdd(&p.stats->filled_outside[p.level], (unsigned long long)__popc(mo));
-                        if (ma) atomicAdd(&p.stats->ambiguous[p.level], (unsigned long long)__popc(ma));
-                    }
-                }
-            } else {
-                uint32_t m = __ballot_sync(FULL, fill_in || fill_out);
-                if (m) {
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(&p.ctr->n_fills[p.level], uint32_t(__popc(m)));
-                    base = __shfl_sync(FULL, base, 0);
-                    if (fill_in || fill_out) {
-                        uint32_t slot = base + __popc(m & lanemask_lt());
-                        if (slot < p.cap_fills) {
-                            FillRec fr;
-                            fr.x = cx;
-                            fr.y = cy;
-                            fr.value = 0x7FC00000u | (uint32_t(p.level & 0xff) << 1) | (fill_in ? 1u : 0u) | (0xF6u << 9);
-                            p.fills[slot] = fr;
-                        } else {
-                            atomicOr(&p.ctr->error, 2u);
-                        }
-                    }
-                }
-                if (p.stats) {
-                    uint32_t mv = __ballot_sync(FULL, valid), mi = __ballot_sync(FULL, fill_in),
-                             mo = __ballot_sync(FULL, fill_out), ma = __ballot_sync(FULL, amb);
-                    if (lane == 0) {
-                        atomicAdd(&p.stats->evaluated[p.level], (unsigned long long)__popc(mv));
-                        if (mi) atomicAdd(&p.stats->filled_inside[p.level], (unsigned long long)__popc(mi));
-                        if (mo) atomicAdd(&p.stats->filled_outside[p.level], (unsigned long long)__popc(mo));
-                        if (ma) atomicAdd(&p.stats->ambiguous[p.level], (unsigned long long)__popc(ma));
-                    }
-                }
-            }
-
-            // simplification (render/mod.rs:96-152: keep the child only if it is shorter)
-            TapeRef child = tr;
-            const bool need = amb && pk.any_nonboth;
-            const uint32_t mneed = __ballot_sync(FULL, need);
-            if (mneed) {
-                const uint32_t total = __popc(mneed);
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(&p.ctr->arena_top, (unsigned long long)total * tr.n_ops);
-                base = __shfl_sync(FULL, base, 0);
-                if (base + (unsigned long long)total * tr.n_ops > p.arena_cap) {
-                    if (lane == 0) atomicOr(&p.ctr->error, 1u);
-                } else {
-                    const uint32_t rank = __popc(mneed & lanemask_lt());
-                    unsigned long long end = base + (unsigned long long)(rank + 1u) * tr.n_ops;
-                    ChoiceUnpacker cu;
-                    cu.base = cs;
-                    cu.ci = tr.n_choices;
-                    uint32_t n_dev, ref_len, nch;
-                    simplify_lane(tape, tr.n_ops, need, live_s[wib], lane, cu, p.arena + end, n_dev, ref_len, nch);
-                    bool keep = need && ref_len < tr.ref_len;
-                    if (keep) {
-                        child.ptr = p.arena + (end - n_dev);
-                        child.n_ops = n_dev;
-                        child.ref_len = ref_len;
-                        child.n_choices = nch;
-                    }
-                    if (p.stats) {
-                        uint32_t mk = __ballot_sync(FULL, keep);
-                        if (lane == 0 && mk) atomicAdd(&p.stats->simplified[p.level], (unsigned long long)__popc(mk));
-                    }
-                }
-            }
-
-            // queue ambiguous children for the next level
-            const uint32_t mamb = __ballot_sync(FULL, amb);
-            if (mamb) {
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(&p.ctr->n_jobs[p.level + 1], uint32_t(__popc(mamb)));
-                base = __shfl_sync(FULL, base, 0);
-                if (amb) {
-                    uint32_t slot = base + __popc(mamb & lanemask_lt());
-                    if (slot < p.cap_out) {
-                        TileJob o;
-                        o.x = cx;
-                        o.y = cy;
-                        o.z = cz;
-                        o.pad = 0;
-                        o.tape = child;
-                        p.jobs_out[slot] = o;
-                    } else {
-                        atomicOr(&p.ctr->error, 2u);
-                    }
-                }
-            }
-        }
+        level_job<DIM, false>(p, j, n_roots, slots, cs, live_s[wib], lane, 0u);
     }
 }
 

@@ -28,7 +28,7 @@ struct TileJob {
     TapeRef tape;
 };  // 40 bytes
 
-struct FillRec { uint32_t x, y, value; };  // 2D fill: corner + RawDistancePixel bits
+struct FillRec { uint32_t x, y, value, ready; };  // 2D fill: corner + RawDistancePixel bits + this render's ready mark
 
 struct Stats {
     unsigned long long evaluated[MAX_LEVELS];
@@ -46,8 +46,9 @@ struct Counters {
     uint32_t n_jobs[MAX_LEVELS + 1];   // n_jobs[l] = tiles queued FOR level l (parents whose children are evaluated at l)
     uint32_t n_fills[MAX_LEVELS];      // 2D fill records produced by level l
     uint32_t cursor[MAX_LEVELS + 2];   // dynamic work cursors (one per kernel)
-    uint32_t error;                    // bit 0: arena exhausted, bit 1: list overflow
-    uint32_t pad;
+    uint32_t error;                    // bit 0: arena exhausted, bit 1: list overflow, bit 2: fused kernel watchdog
+    uint32_t outstanding;              // fused 2D kernel: interval / pixel jobs queued or running
+    uint32_t fill_cursor[MAX_LEVELS];  // fused 2D kernel: fill records painted so far, per level
     unsigned long long arena_top;      // bump pointer (clauses)
 };
 
@@ -115,6 +116,7 @@ struct LevelParams {
     const uint32_t* root_list;
     uint32_t n_root_list;
     TapeRef root_tape;
+    uint32_t epoch;                // ready mark of this render's job and fill records (never 0)
     // image
     uint32_t width, height, depth;
     float z2d;
@@ -255,6 +257,20 @@ size_t coop_smem_bytes(uint32_t n_ops, uint32_t n_choices, uint32_t n_slots);
 cudaError_t launch_interval_root_coop_2d(const LevelParams& p, int blocks, int threads, cudaStream_t s);
 cudaError_t launch_interval_root_coop_3d(const LevelParams& p, int blocks, int threads, cudaStream_t s);
 void launch_pixels_2d(const PixelParams& p, int blocks, cudaStream_t s);
+// Fused 2D tail (tail2d.cu): every level after the root level, the leaf pixels and the fills in ONE
+// persistent launch that drains a dependency-ordered queue
+constexpr int TAIL_MAX_LEVELS = 4;
+struct Tail2DParams {
+    int n_levels;                      // interval levels handled here (levels 1 .. n_levels of the render)
+    LevelParams lv[TAIL_MAX_LEVELS];   // lv[k] = parameters of render level k + 1
+    PixelParams px;
+    uint32_t fill_tile[TAIL_MAX_LEVELS + 1];        // tile edge of the fill records of render level l
+    const FillRec* fills[TAIL_MAX_LEVELS + 1];
+    uint32_t fill_cap[TAIL_MAX_LEVELS + 1];
+    uint32_t epoch;
+};
+cudaError_t launch_tail_2d(const Tail2DParams& p, int sm_count, cudaStream_t s);
+int tail_2d_blocks(int sm_count);
 void launch_fill_2d(const FillParams& p, int blocks, cudaStream_t s);
 
 // trait-level evaluators

@@ -108,7 +108,7 @@ int32_t fc_render2d(fc_ctx* c, const fc_tape* tape, const fc_render2d_cfg* cfg, 
     const int bps = env_int("FIDGET_B200_BLOCKS_PER_SM", 6);
     const int grid_blocks = c->sm_count * bps;
     const uint32_t choice_words = (tape->info.choice_count + 15) / 16 + 1;
-    CU(c->choice_scratch.ensure(size_t(grid_blocks) * WARPS_PER_BLOCK * choice_words * 32 * 4));
+    CU(c->choice_scratch.ensure(size_t(std::max(grid_blocks, tail_2d_blocks(c->sm_count))) * WARPS_PER_BLOCK * choice_words * 32 * 4));
     CU(c->arena.ensure(c->arena_bytes));
     CU(c->counters.ensure(sizeof(Counters)));
     CU(c->stats.ensure(sizeof(Stats)));
@@ -151,9 +151,16 @@ int32_t fc_render2d(fc_ctx* c, const fc_tape* tape, const fc_render2d_cfg* cfg, 
     size_t ev = 0;
     if (timing) CU(cudaEventRecord(get_event(c, ev++), s));
     uint32_t launches = 0;
+    if (++c->epoch == 0) c->epoch = 1;
+    // every level after the root level, the leaf pixels and the fills run as ONE persistent launch (tail2d.cu)
+    // unless the caller asks for the per-level launches (FC_FLAG_UNFUSED: per-kernel timings, A/B runs)
+    const bool fused = L >= 2 && L - 1 <= TAIL_MAX_LEVELS && !(cfg->flags & FC_FLAG_UNFUSED) &&
+                       !env_int("FIDGET_B200_NO_FUSE", 0);
+    Tail2DParams tail{};
     for (int l = 0; l < L; ++l) {
         LevelParams p{};
         p.level = l;
+        p.epoch = c->epoch;
         p.tile = ts[l];
         p.n_axis = l ? ts[l - 1] / ts[l] : 0;
         p.is_last = (l == L - 1);
@@ -182,6 +189,12 @@ int32_t fc_render2d(fc_ctx* c, const fc_tape* tape, const fc_render2d_cfg* cfg, 
         p.ctr = c->counters.as<Counters>();
         p.stats = want_stats ? c->stats.as<Stats>() : nullptr;
         p.vb = vb;
+        if (fused) {
+            tail.fill_tile[l] = ts[l];
+            tail.fills[l] = c->fills[l].as<FillRec>();
+            tail.fill_cap[l] = uint32_t(level_tiles[l + 1]);
+            if (l) { tail.lv[l - 1] = p; continue; }
+        }
         int blocks = grid_blocks;
         if (l == 0) {
             uint64_t warps = (n_roots + 31) / 32;
@@ -199,7 +212,7 @@ int32_t fc_render2d(fc_ctx* c, const fc_tape* tape, const fc_render2d_cfg* cfg, 
         if (!coop) launch_interval_level_2d(p, std::max(blocks, 1), s);
         ++launches;
         if (timing) CU(cudaEventRecord(get_event(c, ev++), s));
-        {
+        if (!fused) {
             // the tiles this level proved inside/outside are painted on a second stream while the
             // next (latency-bound) levels run: fills and leaf pixels never touch the same pixel
             FillParams f{};
@@ -231,10 +244,17 @@ int32_t fc_render2d(fc_ctx* c, const fc_tape* tape, const fc_render2d_cfg* cfg, 
         q.cursor = L;
         q.stats = want_stats ? c->stats.as<Stats>() : nullptr;
         q.vb = vb;
-        launch_pixels_2d(q, c->sm_count * env_int("FIDGET_B200_PIXEL_BLOCKS_PER_SM", 8), s);
+        if (fused) {
+            tail.n_levels = L - 1;
+            tail.px = q;
+            tail.epoch = c->epoch;
+            CU(launch_tail_2d(tail, c->sm_count, s));
+        } else {
+            launch_pixels_2d(q, c->sm_count * env_int("FIDGET_B200_PIXEL_BLOCKS_PER_SM", 8), s);
+        }
         ++launches;
     }
-    if (!serial_fill) {
+    if (!serial_fill && !fused) {
         CU(cudaEventRecord(c->ev_join, c->aux_stream));
         CU(cudaStreamWaitEvent(s, c->ev_join, 0));
     }
@@ -280,16 +300,25 @@ int32_t fc_render2d(fc_ctx* c, const fc_tape* tape, const fc_render2d_cfg* cfg, 
         stats->kernel_launches = launches;
         if (timing) {
             float ms = 0;
-            for (int l = 0; l < L; ++l) {
-                cudaEventElapsedTime(&ms, c->events[l], c->events[l + 1]);
-                stats->stage_ms[l] = ms;
+            if (fused) {   // [0] = root level, [12] = the fused tail (levels 1.., leaf pixels, fills)
+                cudaEventElapsedTime(&ms, c->events[0], c->events[1]);
+                stats->stage_ms[0] = ms;
+                cudaEventElapsedTime(&ms, c->events[1], c->events[3]);
+                stats->stage_ms[12] = ms;
+                cudaEventElapsedTime(&ms, c->events[0], c->events[3]);
+                stats->stage_ms[15] = ms;
+            } else {
+                for (int l = 0; l < L; ++l) {
+                    cudaEventElapsedTime(&ms, c->events[l], c->events[l + 1]);
+                    stats->stage_ms[l] = ms;
+                }
+                cudaEventElapsedTime(&ms, c->events[L], c->events[L + 1]);
+                stats->stage_ms[8] = ms;
+                cudaEventElapsedTime(&ms, c->events[L + 1], c->events[L + 2]);
+                stats->stage_ms[9] = ms;
+                cudaEventElapsedTime(&ms, c->events[0], c->events[L + 2]);
+                stats->stage_ms[15] = ms;
             }
-            cudaEventElapsedTime(&ms, c->events[L], c->events[L + 1]);
-            stats->stage_ms[8] = ms;
-            cudaEventElapsedTime(&ms, c->events[L + 1], c->events[L + 2]);
-            stats->stage_ms[9] = ms;
-            cudaEventElapsedTime(&ms, c->events[0], c->events[L + 2]);
-            stats->stage_ms[15] = ms;
         }
     }
     return rc;

@@ -1,0 +1,182 @@
+// Fused tail of fc_render2d: every interval level after the root level, the leaf pixels and the fill
+// painting in ONE persistent launch (one CTA slot per SM x resident CTAs, each warp an independent worker).
+//
+// Launching one kernel per level makes the frame a chain of latency-bound stages: level 1 of prospero 4096^2
+// keeps 763 warps busy for as long as its LONGEST tape takes while 92 % of the GPU idles, and level 2 cannot
+// start before the last of them ends.  Here the work is a dependency-ordered queue instead: a parent tile is
+// a job; finishing it publishes its ambiguous children as jobs of the next level (or as leaf-tile jobs), which
+// any idle warp picks up at once; warps with nothing else to do paint the tiles the interval levels proved
+// inside / outside.  The frame then lasts as long as its critical path (slowest root -> its slowest child ->
+// one leaf tile), not as the sum over levels of the slowest job of each level.
+//
+// Queue protocol (all state in `Counters`, zeroed per render):
+//   * n_jobs[l] / cursor[l]: slots reserved by producers / claimed by consumers of level l (CAS, never
+//     overshooting, so a warp never holds a claim on a job that does not exist yet);
+//   * a job or fill record becomes valid when its ready mark equals this render's epoch -- written after the
+//     fields and a __threadfence(); consumers spin on the mark, then read the record from L2 (__ldcg);
+//   * child tapes are written to whole 128-byte lines of the arena (level_job.cuh), so the cached tape loads
+//     of the interpreters can never hit a line that an SM cached before another SM filled it;
+//   * outstanding = jobs queued or running; a producer adds its children BEFORE retiring itself, so the count
+//     reaches zero exactly when no interval / pixel work is left; fills are drained after that.
+// Every spin is bounded (error bit 2) -- a logic error must not hang the device.
+#include <algorithm>
+
+#include "level_job.cuh"
+
+namespace fdev {
+
+// leaf tile: one warp, two pixels per lane (k_pixels_2d's body)
+__device__ __forceinline__ void pixel_job(const PixelParams& p, const TileJob& job, float2* slots, int lane,
+                                          unsigned long long& shaded) {
+    const uint32_t T = p.tile, npix = T * T;
+    const uint32_t cx = job.x, cy = job.y;
+    const TapeRef tr = job.tape;
+    const uint2* tape = tr.ptr;
+    for (uint32_t base = 0; base < npix; base += 64u) {
+        uint32_t p0 = base + lane, p1 = p0 + 32u;
+        bool v0 = p0 < npix, v1 = p1 < npix;
+        uint32_t i0 = (v0 ? p0 : 0u) % T, j0 = (v0 ? p0 : 0u) / T;
+        uint32_t i1 = (v1 ? p1 : 0u) % T, j1 = (v1 ? p1 : 0u) / T;
+        float x0, y0, z0, x1, y1, z1;
+        xform_f32(p.mat, float(cx + i0), float(cy + j0), p.z2d, x0, y0, z0);
+        xform_f32(p.mat, float(cx + i1), float(cy + j1), p.z2d, x1, y1, z1);
+        const float2 X = make_float2(x0, x1), Y = make_float2(y0, y1), Z = make_float2(z0, z1);
+        float2 r = run_f32x2(tape, tr.n_ops, slots, [&](uint32_t i) {
+            return pick_input(p.vb, i, X, Y, Z, [](float f) { return make_float2(f, f); });
+        });
+        if (r.x != r.x) r.x = nanf_();   // RawDistancePixel::from(f32): canonical NaN (pixel.rs:234-240)
+        if (r.y != r.y) r.y = nanf_();
+        uint32_t gx0 = cx + i0, gy0 = cy + j0, gx1 = cx + i1, gy1 = cy + j1;
+        if (v0 && gx0 < p.width && gy0 < p.height) p.out[size_t(gy0) * p.width + gx0] = r.x;
+        if (v1 && gx1 < p.width && gy1 < p.height) p.out[size_t(gy1) * p.width + gx1] = r.y;
+        shaded += (v0 ? 1 : 0) + (v1 ? 1 : 0);
+    }
+}
+
+// one interval-proven tile painted by one warp
+__device__ __forceinline__ void fill_job(uint32_t T, uint32_t width, uint32_t height, float* out, uint4 rec, int lane) {
+    const float v = __uint_as_float(rec.z);
+    const bool vec_ok = (width % 4u == 0u) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0u) && (T % 4u == 0u);
+    const uint32_t tile_px = T * T;
+    for (uint32_t pix = uint32_t(lane) * 4u; pix < tile_px; pix += 128u) {
+        if (vec_ok) {
+            const uint32_t x = rec.x + pix % T, y = rec.y + pix / T;
+            if (y >= height || x >= width) continue;
+            *reinterpret_cast<float4*>(out + size_t(y) * width + x) = make_float4(v, v, v, v);
+        } else {
+            for (uint32_t k = 0; k < 4u && pix + k < tile_px; ++k) {
+                const uint32_t x = rec.x + (pix + k) % T, y = rec.y + (pix + k) / T;
+                if (x < width && y < height) out[size_t(y) * width + x] = v;
+            }
+        }
+    }
+}
+
+// lane 0: claim the next slot of a list if one is reserved (never beyond the reserved count)
+__device__ __forceinline__ bool try_claim(uint32_t* cursor, uint32_t reserved, uint32_t& idx) {
+    uint32_t c = ld_volatile_u32(cursor);
+    while (c < reserved) {
+        const uint32_t old = atomicCAS(cursor, c, c + 1u);
+        if (old == c) { idx = c; return true; }
+        c = old;
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_tail_2d(const __grid_constant__ Tail2DParams p) {
+    __shared__ uint32_t live_s[WARPS_PER_BLOCK][8][32];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const uint32_t gw = blockIdx.x * WARPS_PER_BLOCK + wib;
+    itv slots[REG_SLOTS];   // the f32 interpreter of the leaf tiles uses the same bytes as float2[REG_SLOTS]
+    Counters* ctr = p.lv[0].ctr;
+    uint32_t* cs = p.lv[0].choice_scratch + size_t(gw) * p.lv[0].choice_words * 32u + lane;
+    const int L = p.n_levels;   // render levels 1 .. L are interval levels here, list L + 1 holds the leaf tiles
+    unsigned long long shaded = 0;
+    uint32_t idle = 0;
+
+    for (;;) {
+        // ---- find work: shallow levels first (they unlock parallelism), then leaf tiles, then fills ----
+        int kind = -1;   // 0 .. L-1: interval level kind + 1; L: leaf tile; 16 + l: fill of render level l; -2: done
+        uint32_t idx = 0;
+        if (lane == 0) {
+            for (int k = 0; k < L && kind < 0; ++k) {
+                const uint32_t res = min(ld_volatile_u32(&ctr->n_jobs[k + 1]), p.lv[k].cap_in);
+                if (try_claim(&ctr->cursor[k + 1], res, idx)) kind = k;
+            }
+            if (kind < 0) {
+                const uint32_t res = min(ld_volatile_u32(&ctr->n_jobs[L + 1]), p.lv[L - 1].cap_out);
+                if (try_claim(&ctr->cursor[L + 1], res, idx)) kind = L;
+            }
+            if (kind < 0) {
+                for (int l = 0; l <= L && kind < 0; ++l) {
+                    const uint32_t res = min(ld_volatile_u32(&ctr->n_fills[l]), p.fill_cap[l]);
+                    if (try_claim(&ctr->fill_cursor[l], res, idx)) kind = 16 + l;
+                }
+            }
+            if (kind < 0 && ld_volatile_u32(&ctr->outstanding) == 0u) {
+                // no interval / pixel job is queued or running, so every list is final: leave once the fills are claimed
+                bool fills_left = false;
+                for (int l = 0; l <= L; ++l)
+                    fills_left |= ld_volatile_u32(&ctr->fill_cursor[l]) < min(ld_volatile_u32(&ctr->n_fills[l]), p.fill_cap[l]);
+                if (!fills_left) kind = -2;
+            }
+        }
+        kind = __shfl_sync(FULL, kind, 0);
+        idx = __shfl_sync(FULL, idx, 0);
+        if (kind == -2) break;
+        if (kind < 0) {
+            __nanosleep(100);
+            if (++idle > (1u << 22)) {   // watchdog: seconds of fruitless polling
+                if (lane == 0) atomicOr(&ctr->error, 4u);
+                break;
+            }
+            continue;
+        }
+        idle = 0;
+        if (kind < L) {
+            level_job<2, true>(p.lv[kind], idx, 0u, slots, cs, live_s[wib], lane, p.epoch);
+            __syncwarp();
+            if (lane == 0) { __threadfence(); atomicSub(&ctr->outstanding, 1u); }   // children were added before
+        } else if (kind == L) {
+            const TileJob job = load_job_ready(p.px.jobs + idx, p.epoch, ctr);
+            pixel_job(p.px, job, reinterpret_cast<float2*>(slots), lane, shaded);
+            __syncwarp();
+            if (lane == 0) atomicSub(&ctr->outstanding, 1u);
+        } else {
+            const int l = kind - 16;
+            const uint4* rp = reinterpret_cast<const uint4*>(p.fills[l] + idx);
+            uint4 rec = __ldcg(rp);
+            uint32_t spins = 0;
+            while (rec.w != p.epoch) {   // reserved but not written yet
+                __nanosleep(64);
+                rec = __ldcg(rp);
+                if (++spins > (1u << 22)) { atomicOr(&ctr->error, 4u); break; }
+            }
+            if (rec.w == p.epoch) fill_job(p.fill_tile[l], p.px.width, p.px.height, p.px.out, rec, lane);
+        }
+    }
+    if (p.px.stats) {
+        for (int o = 16; o > 0; o >>= 1) shaded += __shfl_xor_sync(FULL, shaded, o);
+        if (lane == 0 && shaded) atomicAdd(&p.px.stats->pixels, shaded);
+    }
+}
+
+cudaError_t launch_tail_2d(const Tail2DParams& p, int sm_count, cudaStream_t s) {
+    static int per_sm = 0;
+    if (!per_sm) {
+        // every CTA must be resident: workers wait for each other's output
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tail_2d, WARPS_PER_BLOCK * 32, 0);
+        if (e != cudaSuccess) return e;
+        per_sm = std::max(1, std::min(per_sm, 8));
+    }
+    k_tail_2d<<<sm_count * per_sm, WARPS_PER_BLOCK * 32, 0, s>>>(p);
+    return cudaGetLastError();
+}
+int tail_2d_blocks(int sm_count) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tail_2d, WARPS_PER_BLOCK * 32, 0) != cudaSuccess) return 0;
+    return sm_count * std::max(1, std::min(per_sm, 8));
+}
+
+}  // namespace fdev

@@ -143,6 +143,8 @@ int32_t fc_simplify(fc_eval* e, const fc_tape* parent, const uint8_t* choices, s
 #define FC_MAX_VARS 16
 #define FC_FLAG_ASYNC 1u        /* enqueue only; errors surface in fc_ctx_synchronize */
 #define FC_FLAG_TIMING 2u       /* record per-stage CUDA events (fc_render_stats.stage_ms) */
+#define FC_FLAG_UNFUSED 8u      /* fc_render2d: one launch per level + leaf + fill kernels instead of the fused persistent tail
+                                   (diagnostics: per-kernel stage_ms) */
 #define FC_FLAG_NO_CLAMP 4u     /* fc_render3d: skip the final depth clamp (slab renders; fc_merge_slabs applies it) */
 
 #define FC_OUT_F32 0u          /* width*height RawDistancePixel bits as f32 (pixel::render's own output) */
@@ -207,7 +209,7 @@ typedef struct fc_render_stats {
     uint64_t arena_bytes_used;
     uint32_t kernel_launches;
     float stage_ms[16];                          /* FC_FLAG_TIMING: interval levels 0..7, then [8]=fill,
-                                                    [9]=bulk f32, [10]=grad, [11]=merge, [15]=total */
+                                                    [9]=bulk f32, [10]=grad, [11]=merge, [12]=fused 2D tail (levels 1.., leaf pixels, fills), [15]=total */
 } fc_render_stats;
 
 /* pixel::render (fidget-raster/src/pixel.rs:452-492).  out: width*height
