@@ -13,6 +13,6 @@ Layout
 from .host import Context, TapeData, Bytecode, OPCODES  # noqa: F401
 from .shape import (  # noqa: F401
     CudaContext, CudaShape, CudaError, RenderConfig2D, RenderConfig3D, GEOMETRY_PIXEL,
-    render2d, render3d, octree_sample, schedule_check, OCTREE_LEAF, pixel_inside, screen_to_world_2d, screen_to_world_3d, pixel_mat, voxel_mat,
+    render2d, render3d, octree_sample, mesh, schedule_check, OCTREE_LEAF, pixel_inside, screen_to_world_2d, screen_to_world_3d, pixel_mat, voxel_mat,
 )
 from . import effects  # noqa: F401,E402

@@ -89,6 +89,11 @@ class FcOctreeStats(C.Structure):
         return d
 
 
+class FcMeshInfo(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("n_leaves", "n_vertices", "n_triangles", "open_edges")] + \
+               [("sampler_ms", C.c_float), ("mesh_ms", C.c_float)]
+
+
 FC_FLAG_ASYNC = 1
 FC_FLAG_TIMING = 2
 FC_FLAG_NO_CLAMP = 4
@@ -129,6 +134,9 @@ CUDA_API = {
     "fc_tiles_pack": (_i32, [_vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp]),
     "fc_tiles_unpack": (_i32, [_vp, _vp, _u32, _u32, _u32, _u32, _u32, _vp]),
     "fc_octree_sample": (_i32, [_vp, _vp, _P(FcOctreeCfg), _vp, _u64, _P(_u64), _P(FcOctreeStats)]),
+    "fc_mesh_build": (_i32, [_vp, _vp, _P(FcOctreeCfg), _P(FcMeshInfo)]),
+    "fc_mesh_read": (_i32, [_vp, _vp, _vp]),
+    "fc_mesh_write_stl": (_i32, [_vp, _vp, C.c_size_t, _P(C.c_size_t)]),
     "fc_schedule_check": (_i32, [_P(_u32), C.c_size_t, _u8, _u32, _u32, _u32, _P(FcScheduleInfo)]),
     "fc_denoise_normals": (_i32, [_vp, _vp, _u32, _u32, _vp]),
     "fc_compute_ssao": (_i32, [_vp, _vp, _u32, _u32, _u32, _vp, _u32, _vp, _u32, _vp]),

@@ -124,6 +124,10 @@ void fc_ctx_destroy(fc_ctx* c) {
     c->leaf_tapes.release();
     c->zsort.release();
     c->root_list.release();
+    c->mesh_leaves.release();
+    c->mesh_scratch.release();
+    c->mesh_verts.release();
+    c->mesh_tris.release();
     c->tile_slots.release();
     c->fx_in.release();
     c->fx_out.release();

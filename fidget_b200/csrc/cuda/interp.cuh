@@ -29,6 +29,14 @@ __device__ __forceinline__ T pick_input(const VarBind& vb, uint32_t i, T X, T Y,
     return from_float(vb.values[k & (MAX_RENDER_VARS - 1)]);
 }
 
+// Clause loads: tapes that were complete before the launch go through the read-only path (ld.global.nc);
+// in the fused 2D kernel a tape may have been written by another SM during the same launch, so it is
+// read with plain loads (its 128-byte lines are exclusive to it and were never cached before).
+template <bool NC>
+__device__ __forceinline__ uint2 ld_clause(const uint2* p) {
+    return NC ? __ldg(p) : *p;
+}
+
 struct Dec {
     uint32_t op, form, out, lhs, rhs;
     Dec() = default;
@@ -46,13 +54,13 @@ struct Dec {
 // Interval interpreter.  `Input` maps a variable index to an interval,
 // `Sink` receives one choice per choice clause in evaluation order, `Out`
 // receives (output index, value).
-template <class Input, class Sink, class Out>
+template <bool NC = true, class Input, class Sink, class Out>
 __device__ __forceinline__ void run_interval(const uint2* __restrict__ tape, uint32_t n_ops, itv* slots,
                                              Input input, Sink& sink, Out out_fn) {
     if (n_ops == 0) return;
-    uint2 w = __ldg(tape);
+    uint2 w = ld_clause<NC>(tape);
     for (uint32_t i = 0; i < n_ops; ++i) {
-        uint2 nxt = __ldg(tape + (i + 1 < n_ops ? i + 1 : i));
+        uint2 nxt = ld_clause<NC>(tape + (i + 1 < n_ops ? i + 1 : i));
         Dec d(w.x);
         float imm = __uint_as_float(w.y);
         itv sl = slots[d.lhs], sr = slots[d.rhs];
@@ -109,14 +117,14 @@ __device__ __forceinline__ float2 f32x2_binary(uint32_t op, float2 a, float2 b) 
     }
 }
 
-template <class Input>
+template <bool NC = true, class Input>
 __device__ __forceinline__ float2 run_f32x2(const uint2* __restrict__ tape, uint32_t n_ops, float2* slots,
                                             Input input) {
     float2 result = make_float2(nanf_(), nanf_());
     if (n_ops == 0) return result;
-    uint2 w = __ldg(tape);
+    uint2 w = ld_clause<NC>(tape);
     for (uint32_t i = 0; i < n_ops; ++i) {
-        uint2 nxt = __ldg(tape + (i + 1 < n_ops ? i + 1 : i));
+        uint2 nxt = ld_clause<NC>(tape + (i + 1 < n_ops ? i + 1 : i));
         Dec d(w.x);
         float imm = __uint_as_float(w.y);
         float2 sl = slots[d.lhs], sr = slots[d.rhs];
@@ -191,7 +199,7 @@ struct ByteChoiceSource {
 // Reverse liveness pass + compaction (VmData::simplify on a register tape that
 // keeps the parent's register assignment).  Writes the child tape backwards,
 // ending at `wend`.  `live` is this warp's [8][32] bitset in shared memory.
-template <class ChoiceSrc>
+template <bool NC = true, class ChoiceSrc>
 __device__ __forceinline__ void simplify_lane(const uint2* __restrict__ tape, uint32_t n_ops, bool active,
                                               uint32_t (*live)[32], int lane, ChoiceSrc& cs, uint2* wend,
                                               uint32_t& n_dev, uint32_t& ref_len, uint32_t& n_choices) {
@@ -202,10 +210,10 @@ __device__ __forceinline__ void simplify_lane(const uint2* __restrict__ tape, ui
     auto clear = [&](uint32_t r) { live[r >> 5][lane] &= ~(1u << (r & 31u)); };
     uint2* wp = wend;
     uint32_t ref = 0, nch = 0;
-    uint2 nxt = n_ops ? __ldg(tape + (n_ops - 1)) : make_uint2(0, 0);
+    uint2 nxt = n_ops ? ld_clause<NC>(tape + (n_ops - 1)) : make_uint2(0, 0);
     for (int i = int(n_ops) - 1; i >= 0; --i) {
         const uint2 w = nxt;
-        if (i > 0) nxt = __ldg(tape + (i - 1));   // prefetch: the clause stream is the latency chain here
+        if (i > 0) nxt = ld_clause<NC>(tape + (i - 1));   // prefetch: the clause stream is the latency chain here
         Dec d(w.x);
         uint32_t c = 3u;
         bool is_choice = op_is_choice(d.op);

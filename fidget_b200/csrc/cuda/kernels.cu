@@ -43,7 +43,6 @@ k_interval_level(const __grid_constant__ LevelParams p) {
 
     const uint32_t n_roots = root_count(p, DIM == 3);
     const uint32_t n_jobs = p.root_mode ? (n_roots + 31u) / 32u : min(p.ctr->n_jobs[p.level], p.cap_in);
-    const uint32_t T = p.tile;
 
     for (;;) {
         uint32_t j = 0;
@@ -51,7 +50,7 @@ k_interval_level(const __grid_constant__ LevelParams p) {
         j = __shfl_sync(FULL, j, 0);
         if (j >= n_jobs) break;
 
-        level_job<DIM, false>(p, j, n_roots, slots, cs, live_s[wib], lane, 0u);
+        level_job<DIM, false>(p, j, n_roots, slots, cs, live_s[wib], lane, p.epoch);
     }
 }
 

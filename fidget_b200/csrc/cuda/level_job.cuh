@@ -89,7 +89,7 @@ __device__ __forceinline__ void level_job(const LevelParams& p, uint32_t j, uint
         ChoicePacker pk;
         pk.base = cs;
         itv r = iv_nan();
-        run_interval(
+        run_interval<!FUSED>(
             tape, tr.n_ops, slots,
             [&](uint32_t i) { return pick_input(p.vb, i, vx, vy, vz, [](float f) { return iv1(f); }); }, pk,
             [&](uint32_t oi, itv v) { if (oi == 0) r = v; });
@@ -165,8 +165,9 @@ __device__ __forceinline__ void level_job(const LevelParams& p, uint32_t j, uint
             // written for one tape is never one an SM may already hold in L1 for another
             const uint32_t slot_ops = FUSED ? ((tr.n_ops + 15u) & ~15u) : tr.n_ops;
             unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&p.ctr->arena_top, (unsigned long long)total * slot_ops);
+            if (lane == 0) base = atomicAdd(&p.ctr->arena_top, (unsigned long long)total * slot_ops + (FUSED ? 15u : 0u));
             base = __shfl_sync(FULL, base, 0);
+            if (FUSED) base = (base + 15ull) & ~15ull;   // (the root level's tapes end anywhere)
             if (base + (unsigned long long)total * slot_ops > p.arena_cap) {
                 if (lane == 0) atomicOr(&p.ctr->error, 1u);
             } else {
@@ -176,7 +177,7 @@ __device__ __forceinline__ void level_job(const LevelParams& p, uint32_t j, uint
                 cu.base = cs;
                 cu.ci = tr.n_choices;
                 uint32_t n_dev, ref_len, nch;
-                simplify_lane(tape, tr.n_ops, need, live, lane, cu, p.arena + end, n_dev, ref_len, nch);
+                simplify_lane<!FUSED>(tape, tr.n_ops, need, live, lane, cu, p.arena + end, n_dev, ref_len, nch);
                 bool keep = need && ref_len < tr.ref_len;
                 if (keep) {
                     child.ptr = p.arena + (end - n_dev);
@@ -197,6 +198,7 @@ __device__ __forceinline__ void level_job(const LevelParams& p, uint32_t j, uint
             uint32_t base = 0;
             if (lane == 0) {
                 atomicAdd(&p.ctr->outstanding, uint32_t(__popc(mamb)));   // before the jobs become claimable
+                if (FUSED) __threadfence();
                 base = atomicAdd(&p.ctr->n_jobs[p.level + 1], uint32_t(__popc(mamb)));
             }
             base = __shfl_sync(FULL, base, 0);

@@ -1,12 +1,12 @@
 // fc_octree_sample: the sampling half of fidget-mesh's Octree::build.
 #include "capi_internal.h"
 
-extern "C" {
-
-int32_t fc_octree_sample(fc_ctx* c, const fc_tape* tape, const fc_octree_cfg* cfg, fc_octree_leaf* out, uint64_t cap,
-                         uint64_t* n_leaves, fc_octree_stats* stats) {
+// Device half: runs the sampler into `dout` (device memory, `cap` leaves); *n_out = surface leaves found
+// (FC_ERR_INVALID when it exceeds cap).  Takes the context lock.
+int32_t octree_sample_device(fc_ctx* c, const fc_tape* tape, const fc_octree_cfg* cfg, OctreeLeaf* dout, uint64_t cap,
+                             uint32_t* n_out_p, fc_octree_stats* stats) {
     static_assert(sizeof(fc_octree_leaf) == sizeof(OctreeLeaf) && sizeof(OctreeLeaf) == 348, "leaf layout");
-    if (!c || !tape || !cfg || !n_leaves || (!out && cap)) return fail(FC_ERR_INVALID, "null argument");
+    if (!c || !tape || !cfg || !n_out_p) return fail(FC_ERR_INVALID, "null argument");
     if (cfg->depth > FC_MAX_OCTREE_DEPTH) return fail(FC_ERR_INVALID, "octree depth too large");
     if (tape->info.mem_count) return fail(FC_ERR_UNSUPPORTED, "the octree sampler needs a tape without memory spills");
     if (tape->info.n_outputs != 1) return fail(FC_ERR_INVALID, "ShapeTape has multiple outputs");
@@ -32,12 +32,6 @@ int32_t fc_octree_sample(fc_ctx* c, const fc_tape* tape, const fc_octree_cfg* cf
         uint64_t cells = 1ull << (3 * std::min(l, int(D)));   // cells at depth l (the leaf list holds depth-D cells)
         level_cap[l] = std::min<uint64_t>(cells, cap_limit);
         CU(c->jobs[l].ensure(level_cap[l] * sizeof(TileJob)));
-    }
-    const bool out_dev = is_device_ptr(out);
-    OctreeLeaf* dout = reinterpret_cast<OctreeLeaf*>(out);
-    if (!out_dev) {
-        CU(c->image.ensure(std::max<uint64_t>(cap, 1) * sizeof(OctreeLeaf)));
-        dout = c->image.as<OctreeLeaf>();
     }
     CU(c->leaf_tapes.ensure(std::max<uint64_t>(cap, 1) * sizeof(TapeRef)));
     CU(cudaMemsetAsync(c->counters.p, 0, sizeof(Counters) + 64, s));
@@ -103,10 +97,9 @@ int32_t fc_octree_sample(fc_ctx* c, const fc_tape* tape, const fc_octree_cfg* cf
     uint32_t n_out = 0;
     CU(cudaMemcpyAsync(&n_out, d_n_out, 4, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
-    *n_leaves = n_out;
+    *n_out_p = n_out;
     int32_t rc = check_device_errors(c);
     if (n_out > cap) rc = fail(FC_ERR_INVALID, "leaf buffer too small: " + std::to_string(n_out) + " surface leaves");
-    if (!rc && !out_dev && n_out) CU(cudaMemcpy(out, dout, size_t(n_out) * sizeof(OctreeLeaf), cudaMemcpyDeviceToHost));
     if (stats) {
         memset(stats, 0, sizeof *stats);
         Stats h;
@@ -127,6 +120,26 @@ int32_t fc_octree_sample(fc_ctx* c, const fc_tape* tape, const fc_octree_cfg* cf
         stats->kernel_launches = launches;
         if (timing) cudaEventElapsedTime(&stats->total_ms, c->events[0], c->events[1]);
     }
+    return rc;
+}
+
+extern "C" {
+
+int32_t fc_octree_sample(fc_ctx* c, const fc_tape* tape, const fc_octree_cfg* cfg, fc_octree_leaf* out, uint64_t cap,
+                         uint64_t* n_leaves, fc_octree_stats* stats) {
+    if (!c || !tape || !cfg || !n_leaves || (!out && cap)) return fail(FC_ERR_INVALID, "null argument");
+    const bool out_dev = is_device_ptr(out);
+    OctreeLeaf* dout = reinterpret_cast<OctreeLeaf*>(out);
+    if (!out_dev) {
+        std::lock_guard<std::mutex> guard(c->mu);
+        CU(cudaSetDevice(c->device));
+        CU(c->image.ensure(std::max<uint64_t>(cap, 1) * sizeof(OctreeLeaf)));
+        dout = c->image.as<OctreeLeaf>();
+    }
+    uint32_t n_out = 0;
+    int32_t rc = octree_sample_device(c, tape, cfg, dout, cap, &n_out, stats);
+    *n_leaves = n_out;
+    if (!rc && !out_dev && n_out) CU(cudaMemcpy(out, dout, size_t(n_out) * sizeof(OctreeLeaf), cudaMemcpyDeviceToHost));
     return rc;
 }
 

@@ -41,7 +41,7 @@ __device__ __forceinline__ void pixel_job(const PixelParams& p, const TileJob& j
         xform_f32(p.mat, float(cx + i0), float(cy + j0), p.z2d, x0, y0, z0);
         xform_f32(p.mat, float(cx + i1), float(cy + j1), p.z2d, x1, y1, z1);
         const float2 X = make_float2(x0, x1), Y = make_float2(y0, y1), Z = make_float2(z0, z1);
-        float2 r = run_f32x2(tape, tr.n_ops, slots, [&](uint32_t i) {
+        float2 r = run_f32x2<false>(tape, tr.n_ops, slots, [&](uint32_t i) {
             return pick_input(p.vb, i, X, Y, Z, [](float f) { return make_float2(f, f); });
         });
         if (r.x != r.x) r.x = nanf_();   // RawDistancePixel::from(f32): canonical NaN (pixel.rs:234-240)

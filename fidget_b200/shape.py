@@ -459,6 +459,34 @@ def octree_sample(shape: CudaShape, depth: int, world_to_model=None, capacity: i
     return (leaves, st.as_dict()) if stats else leaves
 
 
+def mesh(shape: CudaShape, depth: int, world_to_model=None, var_values=(), stl: bool = False):
+    """``Octree::build(...).walk_dual()`` without cell collapse (fidget-mesh): returns ``(vertices [n,3] float32,
+    triangles [m,3] uint32, info dict)`` -- plus the binary STL bytes (``Mesh::write_stl``) when ``stl``."""
+    lib = shape._lib
+    c = _lib.FcOctreeCfg()
+    c.depth = depth
+    if world_to_model is not None:
+        c.has_transform = 1
+        c.world_to_model[:] = np.ascontiguousarray(world_to_model, dtype=np.float32).reshape(16).tolist()
+    c.flags = _lib.FC_FLAG_TIMING
+    c.n_var_values = len(var_values)
+    for i, v in enumerate(var_values):
+        c.var_values[i] = float(v)
+    info = _lib.FcMeshInfo()
+    _ck(lib.fc_mesh_build(shape.cuda._h, shape._h, C.byref(c), C.byref(info)))
+    verts = np.zeros((info.n_vertices, 3), dtype=np.float32)
+    tris = np.zeros((info.n_triangles, 3), dtype=np.uint32)
+    _ck(lib.fc_mesh_read(shape.cuda._h, _ptr(verts), _ptr(tris)))
+    d = {n: getattr(info, n) for n, _ in info._fields_}
+    if not stl:
+        return verts, tris, d
+    n = C.c_size_t()
+    _ck(lib.fc_mesh_write_stl(shape.cuda._h, None, 0, C.byref(n)))
+    buf = np.zeros(n.value, dtype=np.uint8)
+    _ck(lib.fc_mesh_write_stl(shape.cuda._h, _ptr(buf), n.value, C.byref(n)))
+    return verts, tris, d, buf.tobytes()
+
+
 def pixel_inside(img: np.ndarray) -> np.ndarray:
     """RawDistancePixel::inside (pixel.rs:177-183)."""
     bits = img.view(np.uint32)

@@ -273,6 +273,24 @@ typedef struct fc_octree_stats {
 int32_t fc_octree_sample(fc_ctx* ctx, const fc_tape* tape, const fc_octree_cfg* cfg, fc_octree_leaf* out,
                          uint64_t cap, uint64_t* n_leaves, fc_octree_stats* stats /* may be NULL */);
 
+/* ---- meshing back half (fidget-mesh: QEF vertices, dual walk, STL) ---------------------------------------- */
+/* fc_mesh_build = fc_octree_sample + the rest of the Manifold Dual Contouring pipeline on the device, the mesh
+ * staying in HBM until it is read: one vertex per connected group of inside corners of every surface leaf,
+ * positioned by QuadraticErrorSolver::solve (fidget-mesh/src/qef.rs:67-168); four triangles around every
+ * sign-changing cell edge as in dc_edge (fidget-mesh/src/dc.rs:104-213).  Cell collapse (octree.rs:252-440) is
+ * not performed: the result is the uniform-depth mesh (same surface, more triangles in flat regions than the
+ * reference's adaptive one).  Edges on the boundary of the [-1,1]^3 domain get no triangles (open_edges). */
+typedef struct fc_mesh_info {
+    uint64_t n_leaves, n_vertices, n_triangles, open_edges;
+    float sampler_ms, mesh_ms;   /* device time of the sampler / of QEF + dual walk */
+} fc_mesh_info;
+int32_t fc_mesh_build(fc_ctx* ctx, const fc_tape* tape, const fc_octree_cfg* cfg, fc_mesh_info* info);
+/* vertices: n_vertices * 3 floats, triangles: n_triangles * 3 vertex indices; host or device; either may be NULL */
+int32_t fc_mesh_read(fc_ctx* ctx, float* vertices, uint32_t* triangles);
+/* Mesh::write_stl (fidget-mesh/src/output.rs:7-38): binary STL of the last mesh, assembled on the device.
+ * buf == NULL queries the size (84 + 50 * n_triangles). */
+int32_t fc_mesh_write_stl(fc_ctx* ctx, uint8_t* buf, size_t cap, size_t* n_bytes);
+
 /* ---- diagnostics ---------------------------------------------------------- */
 /* Host-only (no device needed): builds the level-0 schedule fc_tape_create would build for this
  * bytecode -- dependency waves, serial / chain tail segments, slot colouring -- and replays it

@@ -261,8 +261,12 @@ def test_random_expressions_all_ops(orc, cuda, seed):
     divisions and cancellations in a random tree)."""
     exact = seed % 2 == 0
     CONT = {"neg", "abs", "recip", "sqrt", "square", "add", "sub", "mul", "div", "min", "max"}
-    ops_u = [o for o in UNARY_OPS if (o not in LIBM_OPS if exact else (o in LIBM_OPS or o in CONT))]
-    ops_b = [o for o in BINARY_OPS if (o not in LIBM_OPS if exact else (o in LIBM_OPS or o in CONT))]
+    # rand / mix hash the BITS of their argument: fed a NaN produced inside the tree they depend on its payload,
+    # which IEEE 754 leaves to the platform (x86 makes 0xFFC00000, CUDA 0x7FFFFFFF) -- the reference's own result is
+    # platform-dependent there.  They are covered with controlled inputs by test_every_op_f32_interval_grad.
+    HASH = {"rand", "mix"}
+    ops_u = [o for o in UNARY_OPS if o not in HASH and (o not in LIBM_OPS if exact else (o in LIBM_OPS or o in CONT))]
+    ops_b = [o for o in BINARY_OPS if o not in HASH and (o not in LIBM_OPS if exact else (o in LIBM_OPS or o in CONT))]
     tapes = []
     for Ctx in (fb.Context, orc.Context):
         ctx = Ctx()
