@@ -418,9 +418,7 @@ def bench_2d(args, torch, fb, cuda, shape, tape, bc, stream, flush, dev, peak, p
     value = SIZE * SIZE / (ms_per_step * 1e-3) / 1e6
 
     # ---- per-kernel timing of one step (CUDA events inside the library, on the launching stream) ----
-    # (FC_FLAG_UNFUSED: one launch per level, so that every kernel has its own duration; the product path fuses
-    #  everything after the root level into one persistent launch, timed below as `fused_stage_ms`)
-    tcfg = fb.RenderConfig2D(SIZE, SIZE, timing=True, unfused=True)
+    tcfg = fb.RenderConfig2D(SIZE, SIZE, timing=True)
     stage = np.zeros(16)
     fstage = np.zeros(16)
     reps = 5
@@ -429,12 +427,16 @@ def bench_2d(args, torch, fb, cuda, shape, tape, bc, stream, flush, dev, peak, p
         flush.fill_(1)
         _, stats = fb.render2d(shape, tcfg, out=image, stats=True)
         stage += np.array(stats["stage_ms"])
+    # the experimental fused tail (FC_FLAG_FUSED_TAIL), for the record
+    for _ in range(2):
+        fb.render2d(shape, fb.RenderConfig2D(SIZE, SIZE, timing=True, fused_tail=True), out=image, stats=True)
+    for _ in range(reps):
         flush.fill_(1)
-        _, fstats = fb.render2d(shape, fb.RenderConfig2D(SIZE, SIZE, timing=True), out=image, stats=True)
+        _, fstats = fb.render2d(shape, fb.RenderConfig2D(SIZE, SIZE, timing=True, fused_tail=True), out=image, stats=True)
         fstage += np.array(fstats["stage_ms"])
     stage /= reps
     fstage /= reps
-    launches_per_step = int(fstats["kernel_launches"])
+    launches_per_step = int(stats["kernel_launches"])
     names = {0: "k_interval_root_coop_2d[L0,128px]", 1: "k_interval_level<2>[L1,32px]",
              2: "k_interval_level<2>[L2,8px]", 8: "k_fill_2d (x3)", 9: "k_pixels_2d"}
     ncu = ncu_table()
@@ -455,10 +457,10 @@ def bench_2d(args, torch, fb, cuda, shape, tape, bc, stream, flush, dev, peak, p
                 "algorithmic_bytes": algo,
                 "definition": "SURVEY 8(d): 4 B per pixel WRITTEN per step / ms_per_step / measured HBM copy bandwidth; "
                               "traffic = sum of the kernels' dram bytes (ncu --set full, profiles/)",
-                "fused_stage_ms": {"k_interval_root_coop_2d[L0,128px]": float(fstage[0]),
-                                   "k_tail_2d (levels 1-2 + leaf pixels + fills, one persistent launch)": float(fstage[12])},
-                "unfused_total_ms": float(stage[15]),
-                "kernels_unfused": kernels}
+                "stage_total_ms": float(stage[15]),
+                "kernels": kernels,
+                "experimental_fused_tail_ms": {"k_interval_root_coop_2d[L0,128px]": float(fstage[0]),
+                                               "k_tail_2d (levels 1-2 + leaf pixels + fills, one persistent launch)": float(fstage[12])}}
 
     # ---- end to end through the public API with HOST buffers ----
     host_img = torch.empty((SIZE, SIZE), dtype=torch.float32).pin_memory()

@@ -95,8 +95,10 @@ __global__ void __launch_bounds__(TMA_THREADS) k_slice_tma(const __grid_constant
     auto run = [&](const float4* in /* [nv] strided by TMA_THREADS, already offset by tid */, uint32_t in_stride,
                    float4& res0, float4& res1) {
         float4* my = slots + tid;
+        uint2 nxt = tape_s[0];
         for (uint32_t i = 0; i < p.n_ops; ++i) {
-            const uint2 w = tape_s[i];
+            const uint2 w = nxt;
+            nxt = tape_s[i + 1 < p.n_ops ? i + 1 : i];   // the clause stream stays one LDS ahead of the arithmetic
             Dec d(w.x);
             const float imm = __uint_as_float(w.y);
             float4 r;

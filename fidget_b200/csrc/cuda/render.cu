@@ -152,10 +152,9 @@ int32_t fc_render2d(fc_ctx* c, const fc_tape* tape, const fc_render2d_cfg* cfg, 
     if (timing) CU(cudaEventRecord(get_event(c, ev++), s));
     uint32_t launches = 0;
     if (++c->epoch == 0) c->epoch = 1;
-    // every level after the root level, the leaf pixels and the fills run as ONE persistent launch (tail2d.cu)
-    // unless the caller asks for the per-level launches (FC_FLAG_UNFUSED: per-kernel timings, A/B runs)
-    const bool fused = L >= 2 && L - 1 <= TAIL_MAX_LEVELS && !(cfg->flags & FC_FLAG_UNFUSED) &&
-                       !env_int("FIDGET_B200_NO_FUSE", 0);
+    // experimental (FC_FLAG_FUSED_TAIL): every level after the root level, the leaf pixels and the fills as ONE
+    // persistent launch draining a job queue (tail2d.cu); the default is one launch per stage
+    const bool fused = L >= 2 && L - 1 <= TAIL_MAX_LEVELS && ((cfg->flags & FC_FLAG_FUSED_TAIL) || env_int("FIDGET_B200_FUSE", 0));
     Tail2DParams tail{};
     for (int l = 0; l < L; ++l) {
         LevelParams p{};

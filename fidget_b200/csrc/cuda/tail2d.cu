@@ -72,19 +72,18 @@ __device__ __forceinline__ void fill_job(uint32_t T, uint32_t width, uint32_t he
     }
 }
 
-// lane 0: claim the next slot of a list if one is reserved (never beyond the reserved count)
-__device__ __forceinline__ bool try_claim(uint32_t* cursor, uint32_t reserved, uint32_t& idx) {
-    uint32_t c = ld_volatile_u32(cursor);
-    while (c < reserved) {
-        const uint32_t old = atomicCAS(cursor, c, c + 1u);
-        if (old == c) { idx = c; return true; }
-        c = old;
-    }
-    return false;
-}
+// Work lists are claimed with TICKETS: a warp that sees unclaimed entries takes the next index with one
+// atomicAdd (a compare-and-swap loop would serialise thousands of idle warps on one address -- measured:
+// 200 ms for a 0.2 ms frame).  When several warps race for the last entries some tickets point past the
+// reserved count; such a ticket is simply kept (one pending ticket per list and warp) and honoured as soon as a
+// producer reserves that index -- or dropped at termination if that never happens.  A warp never blocks on a
+// pending ticket: it keeps looking for other work, so no cycle of waiting warps can form.
+constexpr uint32_t NO_TICKET = 0xffffffffu;
+constexpr int TAIL_LISTS = 2 * TAIL_MAX_LEVELS + 2;   // interval levels, the leaf list, fill levels
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_tail_2d(const __grid_constant__ Tail2DParams p) {
     __shared__ uint32_t live_s[WARPS_PER_BLOCK][8][32];
+    __shared__ uint32_t pend_s[WARPS_PER_BLOCK][TAIL_LISTS];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const uint32_t gw = blockIdx.x * WARPS_PER_BLOCK + wib;
@@ -92,42 +91,61 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_tail_2d(const __grid_c
     Counters* ctr = p.lv[0].ctr;
     uint32_t* cs = p.lv[0].choice_scratch + size_t(gw) * p.lv[0].choice_words * 32u + lane;
     const int L = p.n_levels;   // render levels 1 .. L are interval levels here, list L + 1 holds the leaf tiles
+    uint32_t* pend = pend_s[wib];
+    if (lane < TAIL_LISTS) pend[lane] = NO_TICKET;
+    __syncwarp();
     unsigned long long shaded = 0;
     uint32_t idle = 0;
 
+    // list q: 0 .. L-1 interval level q + 1 (shallow first: they unlock parallelism); L: leaf tiles;
+    //         L + 1 + l: fills of render level l
+    auto cursor_of = [&](int q) -> uint32_t* { return q <= L ? &ctr->cursor[q + 1] : &ctr->fill_cursor[q - L - 1]; };
+    auto reserved_of = [&](int q) -> uint32_t {
+        if (q < L) return min(ld_volatile_u32(&ctr->n_jobs[q + 1]), p.lv[q].cap_in);
+        if (q == L) return min(ld_volatile_u32(&ctr->n_jobs[L + 1]), p.lv[L - 1].cap_out);
+        return min(ld_volatile_u32(&ctr->n_fills[q - L - 1]), p.fill_cap[q - L - 1]);
+    };
+    const int n_lists = 2 * L + 2;
+
     for (;;) {
-        // ---- find work: shallow levels first (they unlock parallelism), then leaf tiles, then fills ----
-        int kind = -1;   // 0 .. L-1: interval level kind + 1; L: leaf tile; 16 + l: fill of render level l; -2: done
+        int kind = -1;   // list index, or -2: done
         uint32_t idx = 0;
         if (lane == 0) {
-            for (int k = 0; k < L && kind < 0; ++k) {
-                const uint32_t res = min(ld_volatile_u32(&ctr->n_jobs[k + 1]), p.lv[k].cap_in);
-                if (try_claim(&ctr->cursor[k + 1], res, idx)) kind = k;
+            // all counters first (independent loads: one L2 round trip), decisions after
+            uint32_t res_v[TAIL_LISTS], cur_v[TAIL_LISTS];
+#pragma unroll
+            for (int q = 0; q < TAIL_LISTS; ++q) {
+                res_v[q] = q < n_lists ? reserved_of(q) : 0u;
+                cur_v[q] = q < n_lists ? ld_volatile_u32(cursor_of(q)) : 0u;
             }
-            if (kind < 0) {
-                const uint32_t res = min(ld_volatile_u32(&ctr->n_jobs[L + 1]), p.lv[L - 1].cap_out);
-                if (try_claim(&ctr->cursor[L + 1], res, idx)) kind = L;
-            }
-            if (kind < 0) {
-                for (int l = 0; l <= L && kind < 0; ++l) {
-                    const uint32_t res = min(ld_volatile_u32(&ctr->n_fills[l]), p.fill_cap[l]);
-                    if (try_claim(&ctr->fill_cursor[l], res, idx)) kind = 16 + l;
+#pragma unroll
+            for (int q = 0; q < TAIL_LISTS; ++q) {
+                if (q >= n_lists || kind >= 0) continue;
+                const uint32_t res = res_v[q];
+                if (pend[q] == NO_TICKET && cur_v[q] < res) pend[q] = atomicAdd(cursor_of(q), 1u);
+                if (pend[q] != NO_TICKET && pend[q] < res) {
+                    kind = q;
+                    idx = pend[q];
+                    pend[q] = NO_TICKET;
                 }
             }
             if (kind < 0 && ld_volatile_u32(&ctr->outstanding) == 0u) {
-                // no interval / pixel job is queued or running, so every list is final: leave once the fills are claimed
-                bool fills_left = false;
-                for (int l = 0; l <= L; ++l)
-                    fills_left |= ld_volatile_u32(&ctr->fill_cursor[l]) < min(ld_volatile_u32(&ctr->n_fills[l]), p.fill_cap[l]);
-                if (!fills_left) kind = -2;
+                // no interval / pixel job is queued or running: every list is final.  Leave once no fill record is
+                // unclaimed and none of this warp's tickets points at an existing one.
+                bool left = false;
+                for (int q = L + 1; q < n_lists; ++q) {
+                    const uint32_t res = reserved_of(q);
+                    left |= ld_volatile_u32(cursor_of(q)) < res || (pend[q] != NO_TICKET && pend[q] < res);
+                }
+                if (!left) kind = -2;
             }
         }
         kind = __shfl_sync(FULL, kind, 0);
         idx = __shfl_sync(FULL, idx, 0);
         if (kind == -2) break;
         if (kind < 0) {
-            __nanosleep(100);
-            if (++idle > (1u << 22)) {   // watchdog: seconds of fruitless polling
+            __nanosleep(200);
+            if (++idle > (1u << 21)) {   // watchdog: about a second of fruitless polling
                 if (lane == 0) atomicOr(&ctr->error, 4u);
                 break;
             }
@@ -144,7 +162,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_tail_2d(const __grid_c
             __syncwarp();
             if (lane == 0) atomicSub(&ctr->outstanding, 1u);
         } else {
-            const int l = kind - 16;
+            const int l = kind - L - 1;
             const uint4* rp = reinterpret_cast<const uint4*>(p.fills[l] + idx);
             uint4 rec = __ldcg(rp);
             uint32_t spins = 0;

@@ -336,7 +336,7 @@ class RenderConfig2D:
     var_values: tuple = ()                      # ShapeVars: value per tape input slot (axis slots ignored)
     interleave: tuple = (0, 0)                  # (N, r): only root tiles with (tx + ty) % N == r (multi-GPU)
     out_format: str = "f32"                     # "f32" | "mask_u8" | "bitmap_1bit" | "rgba8"
-    unfused: bool = False                       # one launch per level instead of the fused persistent tail
+    fused_tail: bool = False                    # experimental: levels 1.., leaf pixels, fills as one persistent launch
 
     def matrix(self):
         return self.mat if self.mat is not None else pixel_mat(self.width, self.height, self.world_to_model)
@@ -379,7 +379,7 @@ def render2d(shape: CudaShape, cfg: RenderConfig2D, out=None, stats: bool = Fals
     for i, t in enumerate(cfg.tile_sizes):
         c.tile_sizes[i] = t
     c.flags = (_lib.FC_FLAG_TIMING if cfg.timing else 0) | (_lib.FC_FLAG_ASYNC if asynchronous else 0) | \
-        (_lib.FC_FLAG_UNFUSED if cfg.unfused else 0)
+        (_lib.FC_FLAG_FUSED_TAIL if cfg.fused_tail else 0)
     c.root_row_begin, c.root_row_end = cfg.root_rows
     c.root_stride, c.root_offset = cfg.interleave
     c.n_var_values = len(cfg.var_values)

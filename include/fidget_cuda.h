@@ -143,8 +143,10 @@ int32_t fc_simplify(fc_eval* e, const fc_tape* parent, const uint8_t* choices, s
 #define FC_MAX_VARS 16
 #define FC_FLAG_ASYNC 1u        /* enqueue only; errors surface in fc_ctx_synchronize */
 #define FC_FLAG_TIMING 2u       /* record per-stage CUDA events (fc_render_stats.stage_ms) */
-#define FC_FLAG_UNFUSED 8u      /* fc_render2d: one launch per level + leaf + fill kernels instead of the fused persistent tail
-                                   (diagnostics: per-kernel stage_ms) */
+#define FC_FLAG_FUSED_TAIL 8u   /* fc_render2d, EXPERIMENTAL: the levels after the root level, the leaf pixels and the fills as one
+                                   persistent launch draining a job queue (tail2d.cu) instead of one launch per stage.
+                                   Same image and census; measured SLOWER on B200 (queue polling hot spot, profiles/), so off
+                                   by default */
 #define FC_FLAG_NO_CLAMP 4u     /* fc_render3d: skip the final depth clamp (slab renders; fc_merge_slabs applies it) */
 
 #define FC_OUT_F32 0u          /* width*height RawDistancePixel bits as f32 (pixel::render's own output) */

@@ -57,7 +57,7 @@ def test_mesh_matches_numpy_oracle(orc, cuda, shape_fn, depth):
     assert len(o_pos) == len(verts)
     cell = 2.0 / 2 ** depth
     d, nn = cKDTree(o_pos).query(verts)
-    assert d.max() < 2e-4 * cell + 1e-6, d.max()            # Jacobi (device) vs SVD (numpy): not bit for bit
+    assert d.max() < 2e-3 * cell, d.max()            # Jacobi in f32 (device) vs SVD in f64 (numpy): not bit for bit
     assert len(np.unique(nn)) == len(verts)
     assert np.array_equal(_canon(nn[tris.astype(np.int64)]), _canon(o_idx))
     assert _manifold(tris)

@@ -737,12 +737,12 @@ def test_solver_style_gradient_batches(orc, cuda):
                                           ("colonnade.vm", 512, (256, 64, 16, 4)), ("prospero.vm", 2048, (64, 8)),
                                           ("bear.vm", 256, (32, 16, 8, 4, 2))])
 def test_fused_tail_equals_per_level_launches(orc, cuda, name, size, ts):
-    """fc_render2d runs the levels after the root level, the leaf pixels and the fills as one persistent launch
-    draining a dependency-ordered queue (tail2d.cu); FC_FLAG_UNFUSED keeps one launch per level.  Same image,
+    """FC_FLAG_FUSED_TAIL (experimental) runs the levels after the root level, the leaf pixels and the fills as one
+    persistent launch draining a dependency-ordered queue (tail2d.cu) instead of one launch per stage.  Same image,
     same census, and both equal the oracle (bear: libm, so the two CUDA paths are compared with each other)."""
     ot, gs = _pair(orc, cuda, name)
-    a, sa = fb.render2d(gs, fb.RenderConfig2D(size, size, tile_sizes=ts), stats=True)
-    b, sb = fb.render2d(gs, fb.RenderConfig2D(size, size, tile_sizes=ts, unfused=True), stats=True)
+    a, sa = fb.render2d(gs, fb.RenderConfig2D(size, size, tile_sizes=ts, fused_tail=True), stats=True)
+    b, sb = fb.render2d(gs, fb.RenderConfig2D(size, size, tile_sizes=ts), stats=True)
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
     for k in ("evaluated", "filled_inside", "filled_outside", "ambiguous", "simplified", "pixels"):
         assert sa[k] == sb[k], k
@@ -752,5 +752,5 @@ def test_fused_tail_equals_per_level_launches(orc, cuda, name, size, ts):
         assert np.array_equal(a.view(np.uint32), o.view(np.uint32))
         assert sa["evaluated"] == so["evaluated"] and sa["simplified"] == so["simplified"]
     for _ in range(3):      # the queue is rebuilt per render: repeated frames stay identical
-        c = fb.render2d(gs, fb.RenderConfig2D(size, size, tile_sizes=ts))
+        c = fb.render2d(gs, fb.RenderConfig2D(size, size, tile_sizes=ts, fused_tail=True))
         assert np.array_equal(a.view(np.uint32), c.view(np.uint32))
