@@ -123,6 +123,7 @@ void fc_ctx_destroy(fc_ctx* c) {
     c->heightmap.release();
     c->leaf_tapes.release();
     c->zsort.release();
+    c->census.release();
     c->root_list.release();
     c->mesh_leaves.release();
     c->mesh_scratch.release();

@@ -261,7 +261,22 @@ k_interval_root_coop(const __grid_constant__ LevelParams p) {
                 if (amb) atomicAdd(&p.stats->ambiguous[0], 1ull);
             }
         }
-        if (!amb) { __syncthreads(); continue; }
+        auto census = [&](bool kept) {   // exact 3D census record of this root tile (tid 0)
+            if (DIM != 3 || !p.census) return;
+            const uint32_t slot = atomicAdd(&p.ctr->n_census, 1u);
+            if (slot < p.cap_census) {
+                CensusRec r;
+                r.x = uint16_t(cx); r.y = uint16_t(cy); r.z = uint16_t(cz);
+                r.level = 0;
+                r.flags = uint8_t((fill_in ? 1u : (fill_out ? 0u : 2u)) | (kept ? 4u : 0u));
+                p.census[slot] = r;
+            } else atomicOr(&p.ctr->error, 2u);
+        };
+        if (!amb) {
+            if (tid == 0) census(false);
+            __syncthreads();
+            continue;
+        }
 
         TapeRef child = p.root_tape;
         if (s_nonboth) {   // uniform: written before the last barrier
@@ -432,6 +447,7 @@ k_interval_root_coop(const __grid_constant__ LevelParams p) {
                 }
             }
         }
+        if (tid == 0) census(child.ptr != p.root_tape.ptr);
         if (tid == 0) {
             uint32_t slot = atomicAdd(&p.ctr->n_jobs[1], 1u);
             if (slot < p.cap_out) {

@@ -163,6 +163,44 @@ void launch_leaf_zsort(const TileJob* jobs, const uint32_t* n_jobs, uint32_t cap
     k_zsort_scatter<<<296, 256, 0, s>>>(jobs, n_jobs, cap, z0, tile, n_layers, hist, order);
 }
 
+// Exact 3D census (FC_FLAG_EXACT_CENSUS).  The reference walks every root column front to back, depth first, and
+// skips a tile when all of its pixels already hold depth >= top + 1 (voxel.rs:283-293).  Everything visited before
+// a tile B that touches B's pixels lies in front of B, and from in front a pixel can only receive depth > top(B) + 1
+// (a filled tile) or >= top(B) + 1 (a voxel hit at z >= top(B)); from inside B it receives at most top(B) (a voxel)
+// or exactly top(B) + 1 with no leaf id (a filled descendant touching B's top).  So "finished before B was visited"
+// can be read off the FINAL heightmap: depth > top + 1, or depth == top + 1 with a leaf id.  One warp per recorded
+// tile applies that to the tile's footprint; tiles with an unfinished pixel are the ones the reference evaluates.
+// For ambiguous tiles of the last level the unfinished columns x tile edge are the voxels it evaluates
+// (voxel.rs:359-386).
+__global__ void __launch_bounds__(256) k_census_3d(const __grid_constant__ CensusParams p) {
+    const uint32_t n = min(*p.n_recs, p.cap);
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = warp; i < n; i += n_warps) {
+        const CensusRec r = p.recs[i];
+        const uint32_t T = p.tile[r.level], top = uint32_t(r.z) + T;
+        uint32_t open_cols = 0;
+        for (uint32_t q = lane; q < T * T; q += 32u) {
+            const unsigned long long key = p.heightmap[size_t(r.y + q / T) * p.width + r.x + q % T];
+            const uint32_t depth = uint32_t(key >> 32), id = uint32_t(key);
+            const bool done = depth > top + 1u || (depth == top + 1u && id != 0u);
+            open_cols += done ? 0u : 1u;
+        }
+        for (int o = 16; o > 0; o >>= 1) open_cols += __shfl_xor_sync(0xffffffffu, open_cols, o);
+        if (lane != 0 || open_cols == 0) continue;
+        const uint32_t cls = r.flags & 3u;
+        atomicAdd(&p.stats->evaluated[r.level], 1ull);
+        if (cls == 1u) atomicAdd(&p.stats->filled_inside[r.level], 1ull);
+        else if (cls == 0u) atomicAdd(&p.stats->filled_outside[r.level], 1ull);
+        else {
+            atomicAdd(&p.stats->ambiguous[r.level], 1ull);
+            if (r.flags & 4u) atomicAdd(&p.stats->simplified[r.level], 1ull);
+            if (int(r.level) == p.last_level) atomicAdd(&p.stats->pixels, (unsigned long long)open_cols * T);
+        }
+    }
+}
+void launch_census_3d(const CensusParams& p, int blocks, cudaStream_t s) { k_census_3d<<<blocks, 256, 0, s>>>(p); }
+
 // K3: normals + final image.  One thread per pixel; the gradient is evaluated
 // at the surface voxel (x, y, depth - 1) with the tape of the
 // leaf tile that found it (voxel.rs:449-481); lanes of a warp that share a

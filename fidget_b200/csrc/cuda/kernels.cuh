@@ -30,6 +30,11 @@ struct TileJob {
 
 struct FillRec { uint32_t x, y, value, ready; };  // 2D fill: corner + RawDistancePixel bits + this render's ready mark
 
+// One interval-evaluated 3D tile, recorded for the exact census (FC_FLAG_EXACT_CENSUS): the reference visits
+// tiles front to back and skips those whose pixels are all finished (voxel.rs:283-293); which tiles that
+// are is decided afterwards from the final heightmap (k_census_3d)
+struct CensusRec { uint16_t x, y, z; uint8_t level, flags; };   // flags: 0 outside, 1 inside, 2 ambiguous; | 4 simplified tape kept
+
 struct Stats {
     unsigned long long evaluated[MAX_LEVELS];
     unsigned long long filled_inside[MAX_LEVELS];
@@ -49,6 +54,8 @@ struct Counters {
     uint32_t error;                    // bit 0: arena exhausted, bit 1: list overflow, bit 2: fused kernel watchdog
     uint32_t outstanding;              // fused 2D kernel: interval / pixel jobs queued or running
     uint32_t fill_cursor[MAX_LEVELS];  // fused 2D kernel: fill records painted so far, per level
+    uint32_t n_census;                 // exact 3D census: records appended
+    uint32_t pad;
     unsigned long long arena_top;      // bump pointer (clauses)
 };
 
@@ -142,6 +149,8 @@ struct LevelParams {
     float cell_h;
     // 3D
     unsigned long long* heightmap;  // 3D: width*height keys (depth << 32 | leaf job id + 1), atomicMax
+    CensusRec* census;              // exact 3D census records (or null)
+    uint32_t cap_census;
     VarBind vb;
 };
 
@@ -243,6 +252,17 @@ void launch_voxels_3d(const VoxelParams& p, int blocks, cudaStream_t s);
 void launch_leaf_zsort(const TileJob* jobs, const uint32_t* n_jobs, uint32_t cap, uint32_t z0, uint32_t tile,
                        uint32_t n_layers, uint32_t* hist, uint32_t* order, cudaStream_t s);
 void launch_normals_3d(const NormalParams& p, cudaStream_t s);
+struct CensusParams {
+    const CensusRec* recs;
+    const uint32_t* n_recs;
+    uint32_t cap;
+    uint32_t tile[MAX_LEVELS];
+    int last_level;
+    const unsigned long long* heightmap;
+    uint32_t width;
+    Stats* stats;
+};
+void launch_census_3d(const CensusParams& p, int blocks, cudaStream_t s);
 void launch_merge_slabs(const void* const* d_slabs, uint32_t n_slabs, uint32_t n_pixels, uint32_t depth, void* out,
                         cudaStream_t s);
 // tile interleave: rank >= 0 packs that rank's tiles of `src` (an image) into `dst` (its chunk);

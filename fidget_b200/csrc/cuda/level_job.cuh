@@ -157,6 +157,7 @@ __device__ __forceinline__ void level_job(const LevelParams& p, uint32_t j, uint
 
         // simplification (render/mod.rs:96-152: keep the child only if it is shorter)
         TapeRef child = tr;
+        bool kept = false;
         const bool need = amb && pk.any_nonboth;
         const uint32_t mneed = __ballot_sync(FULL, need);
         if (mneed) {
@@ -179,6 +180,7 @@ __device__ __forceinline__ void level_job(const LevelParams& p, uint32_t j, uint
                 uint32_t n_dev, ref_len, nch;
                 simplify_lane<!FUSED>(tape, tr.n_ops, need, live, lane, cu, p.arena + end, n_dev, ref_len, nch);
                 bool keep = need && ref_len < tr.ref_len;
+                kept = keep;
                 if (keep) {
                     child.ptr = p.arena + (end - n_dev);
                     child.n_ops = n_dev;
@@ -189,6 +191,23 @@ __device__ __forceinline__ void level_job(const LevelParams& p, uint32_t j, uint
                     uint32_t mk = __ballot_sync(FULL, keep);
                     if (lane == 0 && mk) atomicAdd(&p.stats->simplified[p.level], (unsigned long long)__popc(mk));
                 }
+            }
+        }
+
+        if (DIM == 3 && p.census) {   // exact census: what this launch evaluated, judged later against the final heightmap
+            const uint32_t mv = __ballot_sync(FULL, valid);
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&p.ctr->n_census, uint32_t(__popc(mv)));
+            base = __shfl_sync(FULL, base, 0);
+            if (valid) {
+                const uint32_t slot = base + __popc(mv & lanemask_lt());
+                if (slot < p.cap_census) {
+                    CensusRec r;
+                    r.x = uint16_t(cx); r.y = uint16_t(cy); r.z = uint16_t(cz);
+                    r.level = uint8_t(p.level);
+                    r.flags = uint8_t((fill_in ? 1u : (fill_out ? 0u : 2u)) | (kept ? 4u : 0u));
+                    p.census[slot] = r;
+                } else atomicOr(&p.ctr->error, 2u);
             }
         }
 

@@ -1,4 +1,6 @@
 // The fused tile renderers: fc_render2d (pixel::render), fc_render3d (voxel::render), fc_merge_slabs.
+#include <cstddef>
+
 #include "capi_internal.h"
 
 // TileSizesRef::new (fidget-raster/src/lib.rs:59-66)
@@ -379,6 +381,17 @@ int32_t fc_render3d(fc_ctx* c, const fc_tape* tape, const fc_render3d_cfg* cfg, 
     }
     const size_t npix = size_t(cfg->width) * cfg->height;
     CU(c->heightmap.ensure(npix * 8));
+    const bool exact_census = (cfg->flags & FC_FLAG_EXACT_CENSUS) != 0;
+    uint64_t cap_census = 0;
+    if (exact_census) {
+        if (!stats) return fail(FC_ERR_INVALID, "FC_FLAG_EXACT_CENSUS needs a stats struct");
+        if (cfg->width % T0 || cfg->height % T0 || d_roots || row0 || row1 != roots_y_all || z_begin || z_end < cfg->depth)
+            return fail(FC_ERR_UNSUPPORTED, "the exact census needs a whole-volume render of an image whose sides are multiples of the root tile");
+        cap_census = n_roots;
+        for (int l = 1; l < L; ++l) { const uint64_t r = ts[l - 1] / ts[l]; cap_census += level_cap[l] * r * r * r; }
+        cap_census = std::min<uint64_t>(cap_census, 64ull << 20);
+        CU(c->census.ensure(cap_census * sizeof(CensusRec)));
+    }
     bool out_dev = is_device_ptr(out);
     void* dimg = out;
     if (!out_dev) {
@@ -428,6 +441,8 @@ int32_t fc_render3d(fc_ctx* c, const fc_tape* tape, const fc_render3d_cfg* cfg, 
         p.ctr = c->counters.as<Counters>();
         p.stats = want_stats ? c->stats.as<Stats>() : nullptr;
         p.heightmap = c->heightmap.as<unsigned long long>();
+        p.census = exact_census ? c->census.as<CensusRec>() : nullptr;
+        p.cap_census = uint32_t(cap_census);
         p.vb = vb;
         int blocks = grid_blocks;
         if (l == 0) {
@@ -470,6 +485,23 @@ int32_t fc_render3d(fc_ctx* c, const fc_tape* tape, const fc_render3d_cfg* cfg, 
         q.stats = want_stats ? c->stats.as<Stats>() : nullptr;
         q.vb = vb;
         launch_voxels_3d(q, c->sm_count * env_int("FIDGET_B200_PIXEL_BLOCKS_PER_SM", 8), s);
+        ++launches;
+    }
+    if (exact_census) {
+        // the counts collected so far describe what the device evaluated; replace them by the reference's census,
+        // judged against the final heightmap (k_census_3d)
+        Stats* ds = c->stats.as<Stats>();
+        CU(cudaMemsetAsync(ds, 0, offsetof(Stats, grads), s));                        // evaluated .. simplified, pixels
+        CensusParams cp{};
+        cp.recs = c->census.as<CensusRec>();
+        cp.n_recs = &c->counters.as<Counters>()->n_census;
+        cp.cap = uint32_t(cap_census);
+        for (int l = 0; l < L; ++l) cp.tile[l] = ts[l];
+        cp.last_level = L - 1;
+        cp.heightmap = c->heightmap.as<unsigned long long>();
+        cp.width = cfg->width;
+        cp.stats = ds;
+        launch_census_3d(cp, c->sm_count * 8, s);
         ++launches;
     }
     if (timing) CU(cudaEventRecord(get_event(c, ev++), s));

@@ -754,3 +754,28 @@ def test_fused_tail_equals_per_level_launches(orc, cuda, name, size, ts):
     for _ in range(3):      # the queue is rebuilt per render: repeated frames stay identical
         c = fb.render2d(gs, fb.RenderConfig2D(size, size, tile_sizes=ts, fused_tail=True))
         assert np.array_equal(a.view(np.uint32), c.view(np.uint32))
+
+
+@pytest.mark.parametrize("name,size", [("prospero.vm", 256), ("colonnade.vm", 256), ("tanglecube.vm", 256), ("hi.vm", 128),
+                                       ("colonnade.vm", 512), ("sphere", 128)])
+def test_render3d_exact_census_matches_the_reference_walk(orc, cuda, name, size):
+    """FC_FLAG_EXACT_CENSUS: the per-level tile census (evaluated / filled inside / filled outside / ambiguous /
+    simplified) and the number of voxels evaluated are those of the reference's front-to-back, depth-first walk
+    with its "every pixel already filled" early exit (voxel.rs:244-357) -- although the device evaluates the levels
+    breadth first without that culling.  Equal to the oracle's counts, level by level."""
+    if name == "sphere":
+        ot = orc.Tape.from_data(_sphere_tape(orc.Context, 0.7))
+        gs = fb.CudaShape(cuda, _sphere_tape(fb.Context, 0.7))
+    else:
+        ot, gs = _pair(orc, cuda, name)
+    o_img, o_st = orc.render3d(ot, size, size, size, threads=8)
+    g_img, g_st = fb.render3d(gs, fb.RenderConfig3D(size, size, size, exact_census=True), stats=True)
+    _cmp3d(g_img, o_img, True)
+    for k in ("evaluated", "filled_inside", "filled_outside", "ambiguous", "simplified"):
+        assert g_st[k] == o_st[k], (k, g_st[k], o_st[k])
+    assert g_st["pixels"] == o_st["pixels"]
+    # without the flag the census is what the device evaluated: a superset
+    _, raw = fb.render3d(gs, fb.RenderConfig3D(size, size, size), stats=True)
+    assert all(a >= b for a, b in zip(raw["evaluated"], o_st["evaluated"]))
+    with pytest.raises(fb.CudaError):
+        fb.render3d(gs, fb.RenderConfig3D(100, 100, 100, exact_census=True), stats=True)
