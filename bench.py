@@ -9,7 +9,7 @@ A step = one pass of the hot path over one frame of synthetic input.
           rendered whole on this one GPU, so that every strong-scaling figure has its base in the record.
   N > 1 : ONE fixed workload sharded over the N ranks (strong scaling): models/prospero.vm, 3D render of the
           4096^3 voxel volume (BASELINE.json configs[4]).  Rank r renders the root-tile columns (tx, ty) with
-          (tx + ty) % N == r at full depth, packs its 1/N of the heightmap+normals image, ONE NCCL all-gather
+          hash(tx, ty) % N == r (shard.tile_owner) at full depth, packs its 1/N of the heightmap+normals image, ONE NCCL all-gather
           runs INSIDE the timed region, and every rank unpacks the complete frame.  value = 4096^3 voxels /
           max-over-ranks device time.  Before timing, every rank also renders the whole volume alone and the
           run ASSERTS that the sharded frame is byte-identical to it; rank 0 times that single-GPU render
@@ -377,8 +377,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_3D, "detail": "BASELINE configs[4]; reference VM default tile sizes",
-                       "parallelism": f"{world} ranks, root-tile columns interleaved ((tx+ty) % {world}), full depth per "
-                                      f"column; 1 NCCL all-gather of {img_bytes // world} B per rank inside the timed region",
+                       "parallelism": f"{world} ranks, root-tile columns interleaved (spatial hash % {world}), full depth per "
+                                      f"column; 1 NCCL all-gather of {chunk.numel() * 4} B per rank inside the timed region",
                        "collective": "ncclAllGather (torch.distributed all_gather_into_tensor), 1 per step",
                        "identity_check": "sharded frame == single-GPU frame, byte for byte, asserted on every rank",
                        "l2": "flushed between steps by a 512 MiB fill outside the event-timed regions"},

@@ -38,6 +38,13 @@ constexpr int MEM_BASE = 256;  // memory slot i lives at slot index 256 + i
 __host__ __device__ inline uint32_t enc(uint32_t op, uint32_t form, uint32_t out, uint32_t lhs, uint32_t rhs) {
     return (op * 4u + form) | (out << 8) | (lhs << 16) | (rhs << 24);
 }
+// Multi-GPU tile interleave: which rank renders root tile (tx, ty).  A spatial hash rather than a regular
+// pattern: per-tile cost is heavy-tailed and structured (text lines, silhouettes), and a pseudo-random spread keeps
+// the busiest rank within a few per cent of the mean where the diagonal (tx + ty) % N was 15 % above it at N = 8
+// (prospero, profiles/r02_scaling.md).
+__host__ __device__ inline uint32_t tile_owner(uint32_t tx, uint32_t ty, uint32_t n_ranks) {
+    return ((tx * 73856093u) ^ (ty * 19349663u)) % n_ranks;
+}
 __host__ __device__ inline bool op_is_choice(uint32_t op) { return op >= OP_MIN && op <= OP_OR; }
 __host__ __device__ inline bool op_is_binary(uint32_t op) { return op >= OP_ADD && op <= OP_OR; }
 __host__ __device__ inline bool op_is_unary(uint32_t op) { return op >= OP_NEG && op <= OP_LN; }

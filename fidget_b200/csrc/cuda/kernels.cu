@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(256) k_tiles_copy(const PX* __restrict__ src, 
                                                     uint32_t height, uint32_t T, uint32_t roots_x, const uint32_t* __restrict__ slots,
                                                     uint32_t n_ranks, uint32_t per_rank, int rank) {
     const uint32_t tile = blockIdx.x, tx = tile % roots_x, ty = tile / roots_x;
-    if (rank >= 0 && (tx + ty) % n_ranks != uint32_t(rank)) return;
+    if (rank >= 0 && tile_owner(tx, ty, n_ranks) != uint32_t(rank)) return;
     const uint32_t slot = slots[tile];
     const size_t chunk = size_t(rank >= 0 ? slot - uint32_t(rank) * per_rank : slot) * T * T;
     for (uint32_t q = blockIdx.y * 8u * T + threadIdx.x; q < min((blockIdx.y + 1u) * 8u, T) * T; q += blockDim.x) {

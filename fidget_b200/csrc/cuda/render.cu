@@ -47,13 +47,13 @@ cudaEvent_t get_event(fc_ctx* c, size_t i) {
 }
 
 // Tile interleave of the multi-GPU renders: the XY root tiles (tx, ty) of the band with
-// (tx + ty) % stride == offset, in row-major order, as ids (ty - row0) * roots_x + tx.
+// tile_owner(tx, ty, stride) == offset, in row-major order, as ids (ty - row0) * roots_x + tx.
 static void owned_tiles(uint32_t roots_x, uint32_t row0, uint32_t row1, uint32_t stride, uint32_t offset,
                         std::vector<uint32_t>& ids) {
     ids.clear();
     for (uint32_t ty = row0; ty < row1; ++ty)
         for (uint32_t tx = 0; tx < roots_x; ++tx)
-            if ((tx + ty) % stride == offset) ids.push_back((ty - row0) * roots_x + tx);
+            if (tile_owner(tx, ty, stride) == offset) ids.push_back((ty - row0) * roots_x + tx);
 }
 int32_t root_subset(fc_ctx* c, uint32_t roots_x, uint32_t row0, uint32_t row1, uint32_t stride, uint32_t offset,
                     cudaStream_t s, const uint32_t** d_list, uint32_t* n) {

@@ -334,7 +334,7 @@ class RenderConfig2D:
     root_rows: tuple = (0, 0)                   # band of root-tile rows (multi-GPU)
     timing: bool = False
     var_values: tuple = ()                      # ShapeVars: value per tape input slot (axis slots ignored)
-    interleave: tuple = (0, 0)                  # (N, r): only root tiles with (tx + ty) % N == r (multi-GPU)
+    interleave: tuple = (0, 0)                  # (N, r): only the root tiles rank r of N owns (shard.tile_owner)
     out_format: str = "f32"                     # "f32" | "mask_u8" | "bitmap_1bit" | "rgba8"
     fused_tail: bool = False                    # experimental: levels 1.., leaf pixels, fills as one persistent launch
 
@@ -355,7 +355,7 @@ class RenderConfig3D:
     timing: bool = False
     var_values: tuple = ()
     clamp: bool = True                          # False for slab renders (fc_merge_slabs applies it)
-    interleave: tuple = (0, 0)                  # (N, r): only root-tile columns with (tx + ty) % N == r
+    interleave: tuple = (0, 0)                  # (N, r): only the root-tile columns rank r of N owns
     exact_census: bool = False                  # stats = the reference's front-to-back census (voxel.rs:244-357)
 
     def matrix(self):

@@ -5,7 +5,7 @@ root tiles with the replicated root tape, and ONE collective (an all-gather of t
 follows.  Three partitions:
 
 * **interleaved root tiles** (`render2d_tiles`, `render3d_tiles`; what `bench.py --gpus N` measures): rank r
-  owns the root-tile columns (tx, ty) with (tx + ty) % N == r, at full depth.  Surface-like work is spread
+  owns the root-tile columns (tx, ty) with tile_owner(tx, ty, N) == r (a spatial hash), at full depth.  Surface-like work is spread
   evenly whatever the model looks like, every column keeps its front-to-back culling, each rank
   contributes 1/N of the image to the gather and nothing has to be merged.  The reference's analogue is
   rayon handing root tiles to worker threads (fidget-raster/src/lib.rs:152-165).
@@ -41,10 +41,16 @@ def z_slab(rank: int, world: int, depth: int, root_tile: int = 128):
     return rank * per * root_tile, (rank + 1) * per * root_tile
 
 
+def tile_owner(tx: int, ty: int, world: int) -> int:
+    """Rank that renders root tile (tx, ty): the spatial hash of dev_ops.cuh::tile_owner (a pseudo-random spread
+    balances heavy-tailed per-tile cost better than a regular pattern)."""
+    return (((tx * 73856093) & 0xFFFFFFFF) ^ ((ty * 19349663) & 0xFFFFFFFF)) % world
+
+
 def owned_tiles(rank: int, world: int, width: int, height: int, root_tile: int = 128):
     """Root tiles (tx, ty) of `rank`, row-major: the order of its chunk in the all-gather."""
     rx, ry = (width + root_tile - 1) // root_tile, (height + root_tile - 1) // root_tile
-    return [(tx, ty) for ty in range(ry) for tx in range(rx) if (tx + ty) % world == rank]
+    return [(tx, ty) for ty in range(ry) for tx in range(rx) if tile_owner(tx, ty, world) == rank]
 
 
 def tiles_per_rank(world: int, width: int, height: int, root_tile: int = 128) -> int:

@@ -174,7 +174,8 @@ typedef struct fc_render2d_cfg {
     uint32_t n_var_values;
     float var_values[FC_MAX_VARS];
     /* Multi-GPU tile interleave: with root_stride = N > 1 only the root tiles (tx, ty) with
-     * (tx + ty) % N == root_offset are rendered (the analogue of rayon handing root tiles to worker
+     * ((tx * 73856093) ^ (ty * 19349663)) % N == root_offset (32-bit arithmetic: a spatial hash that spreads
+     * heavy-tailed per-tile cost evenly) are rendered (the analogue of rayon handing root tiles to worker
      * threads, fidget-raster/src/lib.rs:152-165); other pixels are left untouched, and `out` must be a
      * device image.  0 or 1 = every root tile. */
     uint32_t root_stride, root_offset;
