@@ -11,7 +11,7 @@ import fidget_b200 as fb
 
 cuda = fb.CudaContext(0)
 cuda.set_arena_bytes(8 << 30)
-which = sys.argv[1:] or ["bear", "gyroid", "slab", "effects"]
+which = sys.argv[1:] or ["bear", "gyroid", "mesh", "census", "slab", "effects"]
 
 
 def model(name):
@@ -60,6 +60,28 @@ if "gyroid" in which:
                           "wall_ms_incl_d2h_and_sort": wall * 1e3, "Mcells_per_s": 8 ** depth / st["total_ms"] / 1e3,
                           "surface_leaves": len(leaves), "float_points": st["float_points"],
                           "grad_points": st["grad_points"], "ambiguous": st["ambiguous"][:depth + 1]}))
+if "mesh" in which:
+    # fc_mesh_build: sampler + QEF vertices + dual walk, everything resident in HBM; STL assembled on the device
+    shape = fb.CudaShape.from_vm(cuda, model("gyroid-sphere.vm"))
+    for depth in (7, 8, 9):
+        fb.mesh(shape, depth)                      # warm-up (buffers)
+        t0 = time.perf_counter()
+        v, t, info = fb.mesh(shape, depth)
+        wall = time.perf_counter() - t0
+        print(json.dumps({"config": f"gyroid-sphere mesh depth {depth} (fc_mesh_build: sampler + QEF + dual walk on device)",
+                          "sampler_ms": info["sampler_ms"], "qef_and_dual_walk_ms": info["mesh_ms"], "leaves": info["n_leaves"],
+                          "vertices": info["n_vertices"], "triangles": info["n_triangles"], "open_edges": info["open_edges"],
+                          "wall_ms_incl_readback": wall * 1e3, "readback_MB": (v.nbytes + t.nbytes) / 1e6}))
+if "census" in which:
+    # cost of the exact reference census (FC_FLAG_EXACT_CENSUS) on top of a render with statistics
+    shape = fb.CudaShape.from_vm(cuda, model("bear.vm"))
+    n = 1024
+    out = torch.empty((n, n, 4), dtype=torch.float32, device="cuda")
+    a = time_render3d(shape, fb.RenderConfig3D(n, n, n, timing=True), out)
+    b = time_render3d(shape, fb.RenderConfig3D(n, n, n, timing=True, exact_census=True), out)
+    print(json.dumps({"config": "bear.vm 1024^3: device census vs exact reference census", "ms_plain": a["stage_ms"][15],
+                      "ms_exact_census": b["stage_ms"][15], "evaluated_device": a["evaluated"][:5], "evaluated_reference": b["evaluated"][:5],
+                      "voxels_device": a["pixels"], "voxels_reference": b["pixels"]}))
 if "slab" in which:
     shape = fb.CudaShape.from_vm(cuda, model("prospero.vm"))
     n = 4096

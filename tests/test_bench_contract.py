@@ -48,3 +48,54 @@ def test_reference_arm_line():
     assert d["impl"] == "reference" and d["unit"] == "Mvoxels/s" and d["gpu_launches"] == 0
     assert d["e2e"] == {"value": d["value"], "unit": "Mvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] == "port"
+
+
+# ---- round 2 lines: N = 1 is the 2D headline (+ the strong-scaling base), N > 1 is the sharded 4096^3 volume ----
+def _r02(name):
+    p = os.path.join(PROFILES, name)
+    if not os.path.exists(p):
+        pytest.skip(f"{name} not committed yet")
+    with open(p) as f:
+        lines = [l for l in f if l.startswith("{")]
+    return json.loads(lines[-1])
+
+
+def _common(d):
+    for k, ty in BASE.items():
+        assert isinstance(d[k], ty), k
+    assert d["vs_baseline"] is None and d["unit"] == "Mvoxels/s" and d["dtype"] == "f32" and d["higher_is_better"]
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"]) and d["e2e"]["value"] < d["value"]
+    assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(d["clocks"]["reasons"])
+    r = d["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] == "hbm"
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert d["gpu_launches"] > 0
+
+
+def test_r02_n1_line():
+    d = _r02("r02_bench_n1.json")
+    _common(d)
+    assert d["n_gpus"] == 1 and "2D render 4096x4096" in d["config"]["workload"]
+    assert d["value"] == pytest.approx(4096 * 4096 / (d["ms_per_step"] * 1e-3) / 1e6, rel=1e-6)
+    r = d["roofline"]
+    # the headline fraction is the frame's written bytes over the whole step
+    assert r["algorithmic_bytes"] == 4096 * 4096 * 4
+    assert r["achieved"] == pytest.approx(r["algorithmic_bytes"] / (d["ms_per_step"] * 1e-3) / 1e9, rel=1e-6)
+    assert sum(k["frame_bytes_written"] for k in r["kernels"].values()) == r["algorithmic_bytes"]
+    assert {"mask_u8", "bitmap_1bit", "rgba8"} <= set(d["e2e"]["other_output_formats"])
+    b = d["strong_scaling_base"]
+    assert "4096^3" in b["workload"] and b["value"] == pytest.approx(4096 ** 3 / (b["ms_per_step"] * 1e-3) / 1e6, rel=1e-6)
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_r02_sharded_lines(n):
+    d = _r02(f"r02_bench_n{n}.json")
+    _common(d)
+    assert d["n_gpus"] == n and d["scaling"] == "strong" and "3D render 4096^3" in d["config"]["workload"]
+    assert "all-gather" in d["config"]["collective"].lower() or "allgather" in d["config"]["collective"].lower()
+    assert "byte for byte" in d["config"]["identity_check"]
+    assert d["value"] == pytest.approx(4096 ** 3 / (d["ms_per_step"] * 1e-3) / 1e6, rel=1e-6)
+    b = d["strong_scaling_base"]
+    speedup = d["value"] / b["value"]
+    assert 1.0 < speedup <= n * 1.02        # a fixed workload over n ranks
