@@ -75,9 +75,27 @@ inline void* pinned_device_alias(const void* p) {
     return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
 }
 
+// Tuning knobs from the environment.  FIDGET_B200_ENV_LIVE=1 re-reads them on every call (tests flip knobs
+// between renders); otherwise each (name) is read once per process -- no getenv on the render path.
 inline int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v && *v ? atoi(v) : dflt;
+    struct Slot { const char* name; int value; bool set; };
+    static Slot cache[32];
+    static std::mutex mu;
+    static const bool live = [] { const char* v = getenv("FIDGET_B200_ENV_LIVE"); return v && *v && atoi(v) != 0; }();
+    auto read = [&](int d) { const char* v = getenv(name); return v && *v ? atoi(v) : d; };
+    if (live) return read(dflt);
+    std::lock_guard<std::mutex> g(mu);
+    for (auto& sl : cache) {
+        if (sl.name == name) return sl.set ? sl.value : dflt;
+        if (!sl.name) {
+            const char* v = getenv(name);
+            sl.name = name;
+            sl.set = v && *v;
+            sl.value = sl.set ? atoi(v) : 0;
+            return sl.set ? sl.value : dflt;
+        }
+    }
+    return read(dflt);
 }
 
 struct fc_ctx {

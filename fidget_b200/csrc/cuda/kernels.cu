@@ -139,12 +139,20 @@ __global__ void k_zsort_hist(const TileJob* jobs, const uint32_t* n_jobs, uint32
         atomicAdd(&hist[n_layers - 1u - layer], 1u);
     }
 }
-__global__ void k_zsort_scan(uint32_t n_layers, uint32_t* hist) {   // single thread: n_layers <= 4096
-    uint32_t acc = 0;
-    for (uint32_t i = 0; i < n_layers; ++i) {
-        const uint32_t c = hist[i];
-        hist[i] = acc;
-        acc += c;
+// exclusive scan of the layer histogram: one warp, 32 layers per step (shuffle scan + running carry)
+__global__ void k_zsort_scan(uint32_t n_layers, uint32_t* hist) {
+    const uint32_t lane = threadIdx.x;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < n_layers; base += 32u) {
+        const uint32_t i = base + lane;
+        const uint32_t c = i < n_layers ? hist[i] : 0u;
+        uint32_t incl = c;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= uint32_t(o)) incl += v;
+        }
+        if (i < n_layers) hist[i] = carry + incl - c;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
     }
 }
 __global__ void k_zsort_scatter(const TileJob* jobs, const uint32_t* n_jobs, uint32_t cap, uint32_t z0, uint32_t tile,
@@ -159,7 +167,7 @@ void launch_leaf_zsort(const TileJob* jobs, const uint32_t* n_jobs, uint32_t cap
                        uint32_t n_layers, uint32_t* hist, uint32_t* order, cudaStream_t s) {
     cudaMemsetAsync(hist, 0, size_t(n_layers) * 4, s);
     k_zsort_hist<<<296, 256, 0, s>>>(jobs, n_jobs, cap, z0, tile, n_layers, hist);
-    k_zsort_scan<<<1, 1, 0, s>>>(n_layers, hist);
+    k_zsort_scan<<<1, 32, 0, s>>>(n_layers, hist);
     k_zsort_scatter<<<296, 256, 0, s>>>(jobs, n_jobs, cap, z0, tile, n_layers, hist, order);
 }
 

@@ -7,6 +7,7 @@ per-thread kernel it replaces.  Results of the two paths are compared bit for bi
   python scripts/bench_slices.py [log2_n]
 """
 import json, os, sys
+os.environ.setdefault("FIDGET_B200_ENV_LIVE", "1")   # the two paths are selected by an environment knob per call
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch

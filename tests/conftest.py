@@ -4,6 +4,7 @@ import sys
 import numpy as np
 import pytest
 
+os.environ.setdefault("FIDGET_B200_ENV_LIVE", "1")   # tests flip tuning knobs between calls: re-read them every time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 MODELS = os.path.join(ROOT, "models")
