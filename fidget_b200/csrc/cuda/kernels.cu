@@ -31,7 +31,7 @@ namespace fdev {
 // painted later by k_fill_2d).  DIM = 3: voxel::render tiles; an
 // interval-proven-inside tile raises the heightmap to its top + 1
 // (voxel.rs:310-317), heightmap entries are (depth << 32 | leaf job id + 1).
-template <int DIM>
+template <int DIM, bool FUSED_PATH = false>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_interval_level(const __grid_constant__ LevelParams p) {
     __shared__ uint32_t live_s[WARPS_PER_BLOCK][8][32];
@@ -50,12 +50,16 @@ k_interval_level(const __grid_constant__ LevelParams p) {
         j = __shfl_sync(FULL, j, 0);
         if (j >= n_jobs) break;
 
-        level_job<DIM, false>(p, j, n_roots, slots, cs, live_s[wib], lane, p.epoch);
+        level_job<DIM, FUSED_PATH>(p, j, n_roots, slots, cs, live_s[wib], lane, p.epoch);
     }
 }
 
 void launch_interval_level_2d(const LevelParams& p, int blocks, cudaStream_t s) {
-    k_interval_level<2><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(p);
+    // (diagnostic: FIDGET_B200_LEVEL_FUSED_PATH=1 runs the per-level launch with the code path of the fused tail --
+    //  plain tape loads, published jobs, line-aligned arena slots -- to tell code-path cost from scheduling cost)
+    static const bool fused_path = getenv("FIDGET_B200_LEVEL_FUSED_PATH") && atoi(getenv("FIDGET_B200_LEVEL_FUSED_PATH"));
+    if (fused_path && !p.root_mode) k_interval_level<2, true><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(p);
+    else k_interval_level<2><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(p);
 }
 void launch_interval_level_3d(const LevelParams& p, int blocks, cudaStream_t s) {
     k_interval_level<3><<<blocks, WARPS_PER_BLOCK * 32, 0, s>>>(p);

@@ -288,6 +288,7 @@ struct Tail2DParams {
     const FillRec* fills[TAIL_MAX_LEVELS + 1];
     uint32_t fill_cap[TAIL_MAX_LEVELS + 1];
     uint32_t epoch;
+    uint32_t paint_fills;              // 1: idle warps paint the fill records; 0: k_fill_2d launches do (after / beside this kernel)
 };
 cudaError_t launch_tail_2d(const Tail2DParams& p, int sm_count, cudaStream_t s);
 int tail_2d_blocks(int sm_count);

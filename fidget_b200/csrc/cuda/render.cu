@@ -249,7 +249,28 @@ int32_t fc_render2d(fc_ctx* c, const fc_tape* tape, const fc_render2d_cfg* cfg, 
             tail.n_levels = L - 1;
             tail.px = q;
             tail.epoch = c->epoch;
+            tail.paint_fills = env_int("FIDGET_B200_TAIL_PAINTS", 0) ? 1 : 0;
+            auto paint = [&](int l, cudaStream_t fs) {
+                FillParams f{};
+                f.tile = ts[l];
+                f.width = cfg->width; f.height = cfg->height;
+                f.fills = c->fills[l].as<FillRec>();
+                f.n_fills = &c->counters.as<Counters>()->n_fills[l];
+                f.out = dimg;
+                launch_fill_2d(f, c->sm_count * 2, fs);
+                ++launches;
+            };
+            if (!tail.paint_fills) {   // level-0 fills are final already: paint them beside the tail
+                CU(cudaEventRecord(c->ev_fork[0], s));
+                CU(cudaStreamWaitEvent(c->aux_stream, c->ev_fork[0], 0));
+                paint(0, c->aux_stream);
+            }
             CU(launch_tail_2d(tail, c->sm_count, s));
+            if (!tail.paint_fills) {
+                for (int l = 1; l < L; ++l) paint(l, s);
+                CU(cudaEventRecord(c->ev_join, c->aux_stream));
+                CU(cudaStreamWaitEvent(s, c->ev_join, 0));
+            }
         } else {
             launch_pixels_2d(q, c->sm_count * env_int("FIDGET_B200_PIXEL_BLOCKS_PER_SM", 8), s);
         }
@@ -306,6 +327,17 @@ int32_t fc_render2d(fc_ctx* c, const fc_tape* tape, const fc_render2d_cfg* cfg, 
                 stats->stage_ms[0] = ms;
                 cudaEventElapsedTime(&ms, c->events[1], c->events[3]);
                 stats->stage_ms[12] = ms;
+                // when the last job of each list finished inside the fused launch (device clock, ms after its first warp):
+                // [1 .. L-1] interval levels, [L] leaf tiles, [13] level-0 fills .. (statistics of the experiment)
+                if (h.culled[0]) {
+                    for (int k = 1; k <= 2 * (L - 1) + 2 && k < 8; ++k)
+                        stats->stage_ms[k] = h.culled[k] > h.culled[0] ? float(double(h.culled[k] - h.culled[0]) * 1e-6) : 0.0f;
+                    // [8], [9]: latest start of a level-1 / level-2 job; [10], [11]: the longest such job
+                    for (int k = 8; k <= 9; ++k)
+                        stats->stage_ms[k] = h.culled[k] > h.culled[0] ? float(double(h.culled[k] - h.culled[0]) * 1e-6) : 0.0f;
+                    stats->stage_ms[10] = float(double(h.culled[10]) * 1e-6);
+                    stats->stage_ms[11] = float(double(h.culled[11]) * 1e-6);
+                }
                 cudaEventElapsedTime(&ms, c->events[0], c->events[3]);
                 stats->stage_ms[15] = ms;
             } else {

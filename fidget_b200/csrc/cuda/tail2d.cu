@@ -72,18 +72,29 @@ __device__ __forceinline__ void fill_job(uint32_t T, uint32_t width, uint32_t he
     }
 }
 
-// Work lists are claimed with TICKETS: a warp that sees unclaimed entries takes the next index with one
-// atomicAdd (a compare-and-swap loop would serialise thousands of idle warps on one address -- measured:
-// 200 ms for a 0.2 ms frame).  When several warps race for the last entries some tickets point past the
-// reserved count; such a ticket is simply kept (one pending ticket per list and warp) and honoured as soon as a
-// producer reserves that index -- or dropped at termination if that never happens.  A warp never blocks on a
-// pending ticket: it keeps looking for other work, so no cycle of waiting warps can form.
-constexpr uint32_t NO_TICKET = 0xffffffffu;
+// Scheduling.  Work lists are claimed with TICKETS (one atomicAdd on the list cursor hands out a range of
+// indices; a compare-and-swap loop serialised thousands of idle warps on one address: 202 ms for a 0.2 ms
+// frame) and the global queue is watched by ONE warp per CTA at a time (every idle warp polling the counters
+// saturated the L2 slice that also serves the producers' atomics: 1.09 ms).  An idle warp first looks into its
+// CTA's shared-memory ring; if that is empty and no other warp of the CTA is polling, it becomes the CTA's scout:
+// one coalesced read of the reserved / claimed counters of all lists, tickets for as many entries as are
+// available (at most one per warp of the CTA), valid tickets pushed into the ring.  Tickets that point past the
+// reserved count (races between scouts) stay in the CTA's pending range and are honoured as soon as a producer
+// reserves those indices -- a warp never blocks on them, so no cycle of waiting warps can form.
 constexpr int TAIL_LISTS = 2 * TAIL_MAX_LEVELS + 2;   // interval levels, the leaf list, fill levels
+constexpr uint32_t RING = 8;
+
+struct CtaSched {
+    uint32_t ring[RING];        // list << 28 | index
+    uint32_t head, tail;        // consumers advance head (CAS), the scout advances tail
+    uint32_t lock;              // 1 while a warp of this CTA is the scout
+    uint32_t done;
+    uint32_t pend_lo[TAIL_LISTS], pend_hi[TAIL_LISTS];   // tickets taken but not yet handed to a warp
+};
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_tail_2d(const __grid_constant__ Tail2DParams p) {
     __shared__ uint32_t live_s[WARPS_PER_BLOCK][8][32];
-    __shared__ uint32_t pend_s[WARPS_PER_BLOCK][TAIL_LISTS];
+    __shared__ CtaSched sch;
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const uint32_t gw = blockIdx.x * WARPS_PER_BLOCK + wib;
@@ -91,11 +102,15 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_tail_2d(const __grid_c
     Counters* ctr = p.lv[0].ctr;
     uint32_t* cs = p.lv[0].choice_scratch + size_t(gw) * p.lv[0].choice_words * 32u + lane;
     const int L = p.n_levels;   // render levels 1 .. L are interval levels here, list L + 1 holds the leaf tiles
-    uint32_t* pend = pend_s[wib];
-    if (lane < TAIL_LISTS) pend[lane] = NO_TICKET;
-    __syncwarp();
+    if (threadIdx.x == 0) { sch.head = sch.tail = 0; sch.lock = 0; sch.done = 0; }
+    if (threadIdx.x < TAIL_LISTS) { sch.pend_lo[threadIdx.x] = 0; sch.pend_hi[threadIdx.x] = 0; }
+    __syncthreads();
     unsigned long long shaded = 0;
     uint32_t idle = 0;
+    // phase clock (statistics only): when the last job of every list finished, relative to the first warp's start
+    auto now_ns = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+    Stats* st = p.px.stats;
+    if (st && gw == 0 && lane == 0) st->culled[0] = now_ns();
 
     // list q: 0 .. L-1 interval level q + 1 (shallow first: they unlock parallelism); L: leaf tiles;
     //         L + 1 + l: fills of render level l
@@ -105,53 +120,96 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_tail_2d(const __grid_c
         if (q == L) return min(ld_volatile_u32(&ctr->n_jobs[L + 1]), p.lv[L - 1].cap_out);
         return min(ld_volatile_u32(&ctr->n_fills[q - L - 1]), p.fill_cap[q - L - 1]);
     };
-    const int n_lists = 2 * L + 2;
+    const int n_lists = p.paint_fills ? 2 * L + 2 : L + 1;
+    volatile uint32_t* v_head = &sch.head;
+    volatile uint32_t* v_tail = &sch.tail;
+    volatile uint32_t* v_done = &sch.done;
 
     for (;;) {
-        int kind = -1;   // list index, or -2: done
-        uint32_t idx = 0;
+        // ---- 1. the CTA's ring ----
+        uint32_t entry = 0xffffffffu;
         if (lane == 0) {
-            // all counters first (independent loads: one L2 round trip), decisions after
-            uint32_t res_v[TAIL_LISTS], cur_v[TAIL_LISTS];
-#pragma unroll
-            for (int q = 0; q < TAIL_LISTS; ++q) {
-                res_v[q] = q < n_lists ? reserved_of(q) : 0u;
-                cur_v[q] = q < n_lists ? ld_volatile_u32(cursor_of(q)) : 0u;
-            }
-#pragma unroll
-            for (int q = 0; q < TAIL_LISTS; ++q) {
-                if (q >= n_lists || kind >= 0) continue;
-                const uint32_t res = res_v[q];
-                if (pend[q] == NO_TICKET && cur_v[q] < res) pend[q] = atomicAdd(cursor_of(q), 1u);
-                if (pend[q] != NO_TICKET && pend[q] < res) {
-                    kind = q;
-                    idx = pend[q];
-                    pend[q] = NO_TICKET;
-                }
-            }
-            if (kind < 0 && ld_volatile_u32(&ctr->outstanding) == 0u) {
-                // no interval / pixel job is queued or running: every list is final.  Leave once no fill record is
-                // unclaimed and none of this warp's tickets points at an existing one.
-                bool left = false;
-                for (int q = L + 1; q < n_lists; ++q) {
-                    const uint32_t res = reserved_of(q);
-                    left |= ld_volatile_u32(cursor_of(q)) < res || (pend[q] != NO_TICKET && pend[q] < res);
-                }
-                if (!left) kind = -2;
+            for (;;) {
+                const uint32_t h = *v_head, t = *v_tail;
+                if (h == t) break;
+                const uint32_t e = sch.ring[h % RING];     // read before the claim: the slot may be reused right after it
+                if (atomicCAS(&sch.head, h, h + 1u) == h) { entry = e; break; }
             }
         }
-        kind = __shfl_sync(FULL, kind, 0);
-        idx = __shfl_sync(FULL, idx, 0);
-        if (kind == -2) break;
-        if (kind < 0) {
-            __nanosleep(200);
-            if (++idle > (1u << 21)) {   // watchdog: about a second of fruitless polling
-                if (lane == 0) atomicOr(&ctr->error, 4u);
-                break;
+        entry = __shfl_sync(FULL, entry, 0);
+        if (entry == 0xffffffffu) {
+            if (*v_done) break;
+            // ---- 2. become the CTA's scout, or wait for the one that is ----
+            uint32_t scout = 0;
+            if (lane == 0) scout = atomicCAS(&sch.lock, 0u, 1u) == 0u ? 1u : 0u;
+            scout = __shfl_sync(FULL, scout, 0);
+            if (!scout) {
+                // idle warps share their scheduler with latency-bound workers: wake rarely (measured: 200 ns naps of
+                // the seven idle warps per scheduler doubled the duration of the level-1 jobs)
+                __nanosleep(idle < 4u ? 250u : 1500u);
+                if (++idle > (1u << 21)) { if (lane == 0) atomicOr(&ctr->error, 4u); break; }
+                continue;
+            }
+            // one coalesced look at the queue: lane q reads what list q has reserved, lane 16 + q what is claimed
+            // (`outstanding` FIRST: once it reads zero every list is final, so the counters read after it are too)
+            uint32_t outst = lane == 0 ? ld_volatile_u32(&ctr->outstanding) : 0u;
+            outst = __shfl_sync(FULL, outst, 0);
+            __threadfence();
+            const int q_l = lane & 15;
+            uint32_t v = 0;
+            if (q_l < n_lists) v = lane < 16 ? reserved_of(q_l) : ld_volatile_u32(cursor_of(q_l));
+            bool found = false, fills_left = false;
+            for (int q = 0; q < n_lists; ++q) {
+                const uint32_t res = __shfl_sync(FULL, v, q), cur = __shfl_sync(FULL, v, 16 + q);
+                if (lane == 0) {
+                    uint32_t lo = sch.pend_lo[q], hi = sch.pend_hi[q];
+                    const uint32_t space = RING - (*v_tail - *v_head);
+                    if (lo == hi && cur < res && space) {
+                        const uint32_t k = min(min(res - cur, uint32_t(WARPS_PER_BLOCK)), space);
+                        lo = atomicAdd(cursor_of(q), k);
+                        hi = lo + k;
+                    }
+                    uint32_t n_push = (lo < hi && lo < res) ? min(min(hi, res) - lo, space) : 0u;
+                    const uint32_t t = *v_tail;
+                    for (uint32_t i = 0; i < n_push; ++i) sch.ring[(t + i) % RING] = (uint32_t(q) << 28) | (lo + i);
+                    if (n_push) { __threadfence_block(); *v_tail = t + n_push; found = true; }
+                    lo += n_push;
+                    sch.pend_lo[q] = lo;
+                    sch.pend_hi[q] = hi;
+                    if (q > L) fills_left |= cur < res || (lo < hi && lo < res);
+                }
+            }
+            uint32_t flags = (found ? 1u : 0u) | (fills_left ? 2u : 0u);
+            flags = __shfl_sync(FULL, flags, 0);
+            if (lane == 0) {
+                // nothing queued or running and no fill left to paint or to hand out: every list is final and empty
+                if (!(flags & 1u) && outst == 0u && !(flags & 2u) && *v_head == *v_tail) *v_done = 1u;
+                __threadfence_block();
+                atomicExch(&sch.lock, 0u);
+            }
+            if (!(flags & 1u)) {
+                __nanosleep(min(500u << min(idle, 4u), 8000u));   // back off while the queue is dry
+                if (++idle > (1u << 21)) { if (lane == 0) atomicOr(&ctr->error, 4u); break; }
             }
             continue;
         }
         idle = 0;
+        const int kind = int(entry >> 28);
+        const uint32_t idx = entry & 0x0fffffffu;
+        struct Stamp {   // statistics: finishing time of this job in its list's slot; for interval levels also the latest
+            Stats* st; int slot; int lane; unsigned long long t0;      // start and the longest duration
+            __device__ ~Stamp() {
+                if (st && lane == 0) {
+                    unsigned long long t;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                    atomicMax(&st->culled[slot], t);
+                    if (slot <= 2) {
+                        atomicMax(&st->culled[7 + slot], t0);          // [8], [9]: latest start of a level-1 / level-2 job
+                        atomicMax(&st->culled[9 + slot], t - t0);      // [10], [11]: longest level-1 / level-2 job (ns)
+                    }
+                }
+            }
+        } stamp{st, 1 + min(kind, 13), lane, now_ns()};
         if (kind < L) {
             level_job<2, true>(p.lv[kind], idx, 0u, slots, cs, live_s[wib], lane, p.epoch);
             __syncwarp();
