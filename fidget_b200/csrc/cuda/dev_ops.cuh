@@ -80,12 +80,13 @@ FD float f_div_euclid(float a, float b) {
     return q;
 }
 
-// The interpreters inline the few opcodes that make up almost every clause of real tapes (prospero: max, sub, add,
-// min, neg, square, sqrt) and CALL the rest: libm range reductions and the rarer logic inlined into every
-// interpreter loop made the tile kernels 56 KB of code against a 32 KB instruction cache, and the samples of the hot
-// loop showed instruction-fetch stalls.
-static __device__ __noinline__ float f32_unary_cold(uint32_t op, float a) {
+FD float f32_unary(uint32_t op, float a) {
     switch (op) {
+        case OP_NEG: return -a;
+        case OP_ABS: return fabsf(a);
+        case OP_RECIP: return 1.0f / a;
+        case OP_SQRT: return sqrtf(a);
+        case OP_SQUARE: return a * a;
         case OP_FLOOR: return floorf(a);
         case OP_CEIL: return ceilf(a);
         case OP_ROUND: return roundf(a);
@@ -101,35 +102,20 @@ static __device__ __noinline__ float f32_unary_cold(uint32_t op, float a) {
         default: return logf(a);  // OP_LN
     }
 }
-FD float f32_unary(uint32_t op, float a) {
-    switch (op) {
-        case OP_NEG: return -a;
-        case OP_ABS: return fabsf(a);
-        case OP_RECIP: return 1.0f / a;
-        case OP_SQRT: return sqrtf(a);
-        case OP_SQUARE: return a * a;
-        default: return f32_unary_cold(op, a);
-    }
-}
-static __device__ __noinline__ float f32_binary_cold(uint32_t op, float a, float b) {
-    switch (op) {
-        case OP_ATAN2: return atan2f(a, b);
-        case OP_COMPARE: return f_compare(a, b);
-        case OP_MIX: return __uint_as_float(rng_mix(__float_as_uint(a), __float_as_uint(b)));
-        default: return f_rem_euclid(a, b);  // OP_MOD
-    }
-}
 FD float f32_binary(uint32_t op, float a, float b) {
     switch (op) {
         case OP_ADD: return a + b;
         case OP_SUB: return a - b;
         case OP_MUL: return a * b;
         case OP_DIV: return a / b;
+        case OP_ATAN2: return atan2f(a, b);
+        case OP_COMPARE: return f_compare(a, b);
+        case OP_MIX: return __uint_as_float(rng_mix(__float_as_uint(a), __float_as_uint(b)));
+        case OP_MOD: return f_rem_euclid(a, b);
         case OP_MIN: return f_min(a, b);
         case OP_MAX: return f_max(a, b);
         case OP_AND: return a == 0.0f ? a : b;
-        case OP_OR: return a != 0.0f ? a : b;
-        default: return f32_binary_cold(op, a, b);
+        default: return a != 0.0f ? a : b;  // OP_OR
     }
 }
 // Choice of a point evaluation (1 = left, 2 = right, 3 = both)
@@ -281,8 +267,13 @@ FD itv iv_atan2(itv y, itv x) {
     return iv(fminf(fminf(__int_as_float(0x7f800000), v0), v1), fmaxf(fmaxf(__int_as_float(0xff800000), v0), v1));
 }
 
-static __device__ __noinline__ itv iv_unary_cold(uint32_t op, itv a) {
+FD itv iv_unary(uint32_t op, itv a) {
     switch (op) {
+        case OP_NEG: return iv_neg(a);
+        case OP_ABS: return iv_abs(a);
+        case OP_RECIP: return iv_recip(a);
+        case OP_SQRT: return iv_sqrt(a);
+        case OP_SQUARE: return iv_square(a);
         case OP_FLOOR: return iv(floorf(a.x), floorf(a.y));
         case OP_CEIL: return iv(ceilf(a.x), ceilf(a.y));
         case OP_ROUND: return iv(roundf(a.x), roundf(a.y));
@@ -298,24 +289,6 @@ static __device__ __noinline__ itv iv_unary_cold(uint32_t op, itv a) {
         default: return iv_ln(a);
     }
 }
-FD itv iv_unary(uint32_t op, itv a) {
-    switch (op) {
-        case OP_NEG: return iv_neg(a);
-        case OP_ABS: return iv_abs(a);
-        case OP_RECIP: return iv_recip(a);
-        case OP_SQRT: return iv_sqrt(a);
-        case OP_SQUARE: return iv_square(a);
-        default: return iv_unary_cold(op, a);
-    }
-}
-static __device__ __noinline__ itv iv_binary_cold(uint32_t op, itv a, itv b) {
-    switch (op) {
-        case OP_ATAN2: return iv_atan2(a, b);
-        case OP_COMPARE: return iv_compare(a, b);
-        case OP_MIX: return iv_mix(a, b);
-        default: return iv_rem_euclid(a, b);  // OP_MOD
-    }
-}
 // Non-choice binary ops
 FD itv iv_binary(uint32_t op, itv a, itv b) {
     switch (op) {
@@ -323,7 +296,10 @@ FD itv iv_binary(uint32_t op, itv a, itv b) {
         case OP_SUB: return iv_sub(a, b);
         case OP_MUL: return iv_mul(a, b);
         case OP_DIV: return iv_div(a, b);
-        default: return iv_binary_cold(op, a, b);
+        case OP_ATAN2: return iv_atan2(a, b);
+        case OP_COMPARE: return iv_compare(a, b);
+        case OP_MIX: return iv_mix(a, b);
+        default: return iv_rem_euclid(a, b);  // OP_MOD
     }
 }
 // Choice ops: returns the value, writes the choice (1 left, 2 right, 3 both)
@@ -365,8 +341,13 @@ FD grd gr_div(grd a, grd b) {
     return gr(a.x / b.x, (b.x * a.y - a.x * b.y) / d, (b.x * a.z - a.x * b.z) / d, (b.x * a.w - a.x * b.w) / d);
 }
 FD grd gr_scale_div(grd a, float v, float r) { return gr(v, a.y / r, a.z / r, a.w / r); }
-static __device__ __noinline__ grd gr_unary_cold(uint32_t op, grd a) {
+FD grd gr_unary(uint32_t op, grd a) {
     switch (op) {
+        case OP_NEG: return gr_neg(a);
+        case OP_ABS: return a.x < 0.0f ? gr_neg(a) : a;
+        case OP_RECIP: return gr_div(gr1(1.0f), a);
+        case OP_SQRT: { float v = sqrtf(a.x); return gr_scale_div(a, v, 2.0f * v); }
+        case OP_SQUARE: return gr_mul(a, a);
         case OP_FLOOR: return gr1(floorf(a.x));
         case OP_CEIL: return gr1(ceilf(a.x));
         case OP_ROUND: return gr1(roundf(a.x));
@@ -382,18 +363,12 @@ static __device__ __noinline__ grd gr_unary_cold(uint32_t op, grd a) {
         default: return gr_scale_div(a, logf(a.x), a.x);  // OP_LN
     }
 }
-FD grd gr_unary(uint32_t op, grd a) {
+FD grd gr_binary(uint32_t op, grd a, grd b) {
     switch (op) {
-        case OP_NEG: return gr_neg(a);
-        case OP_ABS: return a.x < 0.0f ? gr_neg(a) : a;
-        case OP_RECIP: return gr_div(gr1(1.0f), a);
-        case OP_SQRT: { float v = sqrtf(a.x); return gr_scale_div(a, v, 2.0f * v); }
-        case OP_SQUARE: return gr_mul(a, a);
-        default: return gr_unary_cold(op, a);
-    }
-}
-static __device__ __noinline__ grd gr_binary_cold(uint32_t op, grd a, grd b) {
-    switch (op) {
+        case OP_ADD: return gr_add(a, b);
+        case OP_SUB: return gr_sub(a, b);
+        case OP_MUL: return gr_mul(a, b);
+        case OP_DIV: return gr_div(a, b);
         case OP_ATAN2: {
             float d = b.x * b.x + a.x * a.x;
             return gr(atan2f(a.x, b.x), (b.x * a.y - a.x * b.y) / d, (b.x * a.z - a.x * b.z) / d,
@@ -401,23 +376,14 @@ static __device__ __noinline__ grd gr_binary_cold(uint32_t op, grd a, grd b) {
         }
         case OP_COMPARE: return gr1(f_compare(a.x, b.x));
         case OP_MIX: return gr1(__uint_as_float(rng_mix(__float_as_uint(a.x), __float_as_uint(b.x))));
-        default: {  // OP_MOD
+        case OP_MOD: {
             float e = f_div_euclid(a.x, b.x);
             return gr(f_rem_euclid(a.x, b.x), a.y - b.y * e, a.z - b.z * e, a.w - b.w * e);
         }
-    }
-}
-FD grd gr_binary(uint32_t op, grd a, grd b) {
-    switch (op) {
-        case OP_ADD: return gr_add(a, b);
-        case OP_SUB: return gr_sub(a, b);
-        case OP_MUL: return gr_mul(a, b);
-        case OP_DIV: return gr_div(a, b);
         case OP_MIN: return (a.x != a.x || b.x != b.x) ? gr1(nanf_()) : (a.x < b.x ? a : b);
         case OP_MAX: return (a.x != a.x || b.x != b.x) ? gr1(nanf_()) : (a.x > b.x ? a : b);
         case OP_AND: return a.x == 0.0f ? a : b;
-        case OP_OR: return a.x != 0.0f ? a : b;
-        default: return gr_binary_cold(op, a, b);
+        default: return a.x != 0.0f ? a : b;
     }
 }
 
