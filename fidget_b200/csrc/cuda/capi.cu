@@ -124,6 +124,7 @@ void fc_ctx_destroy(fc_ctx* c) {
     c->leaf_tapes.release();
     c->zsort.release();
     c->census.release();
+    c->occl.release();
     c->root_list.release();
     c->mesh_leaves.release();
     c->mesh_scratch.release();

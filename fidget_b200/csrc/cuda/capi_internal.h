@@ -108,7 +108,7 @@ struct fc_ctx {
     uint64_t arena_bytes = 1ull << 30;
     uint32_t epoch = 0;                       // ready mark of the current render's job / fill records
     // render scratch
-    DevBuf arena, jobs[MAX_LEVELS + 1], fills[MAX_LEVELS], choice_scratch, counters, stats, image, heightmap, leaf_tapes, zsort, census;
+    DevBuf arena, jobs[MAX_LEVELS + 1], fills[MAX_LEVELS], choice_scratch, counters, stats, image, heightmap, leaf_tapes, zsort, census, occl;
     DevBuf mesh_leaves, mesh_scratch, mesh_verts, mesh_tris;   // fc_mesh_build: sampler output and the mesh, resident in HBM
     uint32_t mesh_n_verts = 0, mesh_n_tris = 0;
     DevBuf fx_in, fx_out, fx_tmp, fx_tables;  // effects: staged host images, intermediate maps, SSAO tables

@@ -241,6 +241,9 @@ k_interval_root_coop(const __grid_constant__ LevelParams p) {
                 const uint32_t x = cx + q % T, y = cy + q / T;
                 if (x < p.width && y < p.height) atomicMax(&p.heightmap[size_t(y) * p.width + x], key);
             }
+            if (p.occl && T % 16u == 0u)
+                for (uint32_t q = tid; q < (T / 16u) * (T / 16u); q += NT)
+                    atomicMax(p.occl + size_t(cy / 16u + q / (T / 16u)) * p.occl_w + cx / 16u + q % (T / 16u), cz + T + 1u);
         }
         if (tid == 0) {
             if (DIM == 2 && !amb) {

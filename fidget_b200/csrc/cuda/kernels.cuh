@@ -149,6 +149,12 @@ struct LevelParams {
     float cell_h;
     // 3D
     unsigned long long* heightmap;  // 3D: width*height keys (depth << 32 | leaf job id + 1), atomicMax
+    // 3D occlusion map: per 16 x 16 block of pixels, a lower bound of the depth EVERY pixel of the block already has
+    // (raised by interval-proven-inside tiles that cover whole blocks).  A parent whose blocks all reach its top + 1
+    // cannot show anything: its children are skipped (cull != 0: this level's parents are made of whole blocks).
+    uint32_t* occl;
+    uint32_t occl_w;                // blocks per row
+    uint32_t cull;
     CensusRec* census;              // exact 3D census records (or null)
     uint32_t cap_census;
     VarBind vb;

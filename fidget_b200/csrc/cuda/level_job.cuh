@@ -42,6 +42,7 @@ template <int DIM, bool FUSED>
 __device__ __forceinline__ void level_job(const LevelParams& p, uint32_t j, uint32_t n_roots, itv* slots, uint32_t* cs,
                                           uint32_t (*live)[32], int lane, uint32_t epoch) {
     const uint32_t T = p.tile;
+    bool cull_open = false, cull_check = false;
     TapeRef tr;
     uint32_t px = 0, py = 0, pz = 0, nchild;
     if (p.root_mode) {
@@ -54,6 +55,16 @@ __device__ __forceinline__ void level_job(const LevelParams& p, uint32_t j, uint
         pz = jb.z;
         tr = jb.tape;
         nchild = p.n_axis * p.n_axis * (DIM == 3 ? p.n_axis : 1u);
+        if (DIM == 3 && p.mode != 1u && p.cull) {
+            // Every pixel under this parent already holds depth >= its top + 1 (tiles in front, proven inside by coarser
+            // levels): nothing inside can show, so none of its children is evaluated.  The reference skips the same
+            // tiles in its front-to-back walk (voxel.rs:283-293) -- and more, since it also knows the voxel hits in
+            // front, which arrive last here.  One small read of the occlusion map per lane, not the heightmap itself.
+            const uint32_t nb = (T * p.n_axis) / 16u, need = pz + T * p.n_axis + 1u;   // blocks per side of the parent
+            for (uint32_t q = lane; q < nb * nb; q += 32u)
+                cull_open |= __ldcg(p.occl + size_t(py / 16u + q / nb) * p.occl_w + px / 16u + q % nb) < need;
+            cull_check = true;
+        }
     }
     const uint2* tape = tr.ptr;
 
@@ -86,6 +97,12 @@ __device__ __forceinline__ void level_job(const LevelParams& p, uint32_t j, uint
             xform_iv(p.mat, X, Y, Z, vx, vy, vz);
         }
 
+        if (DIM == 3 && cull_check && chunk == 0) {
+            if (!__any_sync(FULL, cull_open)) {
+                if (p.stats && lane == 0) atomicAdd(&p.stats->culled[p.level], (unsigned long long)nchild);
+                return;
+            }
+        }
         ChoicePacker pk;
         pk.base = cs;
         itv r = iv_nan();
@@ -112,6 +129,9 @@ __device__ __forceinline__ void level_job(const LevelParams& p, uint32_t j, uint
                     const uint32_t x = fx + q % T, y = fy + q / T;
                     if (x < p.width && y < p.height) atomicMax(&p.heightmap[size_t(y) * p.width + x], key);
                 }
+                if (p.occl && T % 16u == 0u)   // the whole blocks this tile covers now hold its depth (the same value the heightmap gets)
+                    for (uint32_t q = lane; q < (T / 16u) * (T / 16u); q += 32u)
+                        atomicMax(p.occl + size_t(fy / 16u + q / (T / 16u)) * p.occl_w + fx / 16u + q % (T / 16u), fz + T + 1u);
             }
             if (p.stats) {
                 uint32_t mv = __ballot_sync(FULL, valid), mi = __ballot_sync(FULL, fill_in),

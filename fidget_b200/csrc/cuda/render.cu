@@ -438,6 +438,14 @@ int32_t fc_render3d(fc_ctx* c, const fc_tape* tape, const fc_render3d_cfg* cfg, 
     }
     CU(cudaMemsetAsync(c->counters.p, 0, sizeof(Counters), s));
     CU(cudaMemsetAsync(c->heightmap.as<char>() + size_t(band_y0) * cfg->width * 8, 0, size_t(band_y1 - band_y0) * cfg->width * 8, s));
+    // occlusion map (16 x 16 pixel blocks); used when every tile size down to 16 is a multiple of 16
+    const uint32_t occl_w = (cfg->width + 15) / 16, occl_h = (cfg->height + 15) / 16;
+    bool use_occl = !env_int("FIDGET_B200_NO_CULL", 0);
+    for (int l = 0; l < L; ++l) if (ts[l] >= 16 && ts[l] % 16) use_occl = false;
+    if (use_occl) {
+        CU(c->occl.ensure(size_t(occl_w) * occl_h * 4));
+        CU(cudaMemsetAsync(c->occl.p, 0, size_t(occl_w) * occl_h * 4, s));
+    }
     if (want_stats) CU(cudaMemsetAsync(c->stats.p, 0, sizeof(Stats), s));
 
     VarBind vb;
@@ -473,6 +481,9 @@ int32_t fc_render3d(fc_ctx* c, const fc_tape* tape, const fc_render3d_cfg* cfg, 
         p.ctr = c->counters.as<Counters>();
         p.stats = want_stats ? c->stats.as<Stats>() : nullptr;
         p.heightmap = c->heightmap.as<unsigned long long>();
+        p.occl = use_occl ? c->occl.as<uint32_t>() : nullptr;
+        p.occl_w = occl_w;
+        p.cull = (use_occl && l >= 1 && ts[l - 1] >= 16u && ts[l - 1] <= 64u) ? 1u : 0u;   // parents made of 1, 4 or 16 blocks
         p.census = exact_census ? c->census.as<CensusRec>() : nullptr;
         p.cap_census = uint32_t(cap_census);
         p.vb = vb;
@@ -516,7 +527,7 @@ int32_t fc_render3d(fc_ctx* c, const fc_tape* tape, const fc_render3d_cfg* cfg, 
         q.list = L; q.cursor = L;
         q.stats = want_stats ? c->stats.as<Stats>() : nullptr;
         q.vb = vb;
-        launch_voxels_3d(q, c->sm_count * env_int("FIDGET_B200_PIXEL_BLOCKS_PER_SM", 8), s);
+        launch_voxels_3d(q, c->sm_count * env_int("FIDGET_B200_VOXEL_BLOCKS_PER_SM", 12), s);
         ++launches;
     }
     if (exact_census) {

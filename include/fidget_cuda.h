@@ -149,7 +149,7 @@ int32_t fc_simplify(fc_eval* e, const fc_tape* parent, const uint8_t* choices, s
                                    by default */
 #define FC_FLAG_EXACT_CENSUS 16u /* fc_render3d with stats: report the tile census and voxel count of the reference's front-to-back
                                    walk (voxel.rs:244-357), computed from the final heightmap; without it the census counts what
-                                   the device evaluated (a superset: no culling behind finished pixels).  Whole-volume renders of
+                                   the device evaluated (a superset: it only culls whole parents behind interval-proven tiles).  Whole-volume renders of
                                    images whose sides are multiples of the root tile */
 #define FC_FLAG_NO_CLAMP 4u     /* fc_render3d: skip the final depth clamp (slab renders; fc_merge_slabs applies it) */
 

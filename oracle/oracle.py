@@ -113,7 +113,7 @@ class Tape:
         self.size, self.ssa_len, self.choice_count, self.slot_count, self.n_vars = [v.value for v in vals]
 
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:   # module globals are gone at interpreter shutdown
             lib().orc_tape_free(self._h)
             self._h = None
 

@@ -11,7 +11,7 @@ import fidget_b200 as fb
 
 cuda = fb.CudaContext(0)
 cuda.set_arena_bytes(8 << 30)
-which = sys.argv[1:] or ["bear", "gyroid", "mesh", "census", "slab", "effects"]
+which = sys.argv[1:] or ["bear", "gyroid", "mesh", "census", "slab", "volume", "effects"]
 
 
 def model(name):
@@ -92,6 +92,16 @@ if "slab" in which:
     print(json.dumps({"config": "prospero.vm 3D 4096^3, front Z slab [3584,4096) of an 8-way split, 1 GPU",
                       "ms": ms[15], "Mvoxels_per_s_slab": n * n * 512 / ms[15] / 1e3, "levels_ms": ms[:5],
                       "voxels_ms": ms[9], "normals_ms": ms[10], "voxel_evals": st["pixels"],
+                      "arena_MB": st["arena_bytes_used"] / 1e6}))
+if "volume" in which:
+    # the N > 1 bench workload on one GPU (bench.py's strong_scaling_base)
+    shape = fb.CudaShape.from_vm(cuda, model("prospero.vm"))
+    n = 4096
+    out = torch.empty((n, n, 4), dtype=torch.float32, device="cuda")
+    st = time_render3d(shape, fb.RenderConfig3D(n, n, n, timing=True), out, reps=4)
+    ms = st["stage_ms"]
+    print(json.dumps({"config": "prospero.vm 3D 4096^3 whole volume, 1 GPU", "ms": ms[15], "levels_ms": ms[:5], "voxels_ms": ms[9],
+                      "normals_ms": ms[10], "voxel_evals": st["pixels"], "evaluated": st["evaluated"][:5],
                       "arena_MB": st["arena_bytes_used"] / 1e6}))
 if "effects" in which:
     # fidget-raster's viewer post-processing on a device-resident bear.vm 1024^3 heightmap:

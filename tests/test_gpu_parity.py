@@ -779,3 +779,22 @@ def test_render3d_exact_census_matches_the_reference_walk(orc, cuda, name, size)
     assert all(a >= b for a, b in zip(raw["evaluated"], o_st["evaluated"]))
     with pytest.raises(fb.CudaError):
         fb.render3d(gs, fb.RenderConfig3D(100, 100, 100, exact_census=True), stats=True)
+
+
+@pytest.mark.parametrize("name,size", [("bear.vm", 512), ("prospero.vm", 512), ("colonnade.vm", 256)])
+def test_render3d_occlusion_culling_changes_nothing_but_the_work(orc, cuda, name, size, monkeypatch):
+    """Parents whose 16 x 16 pixel blocks are all finished in front of them (occlusion map raised by interval-proven
+    tiles) are skipped, like the reference's front-to-back walk skips them (voxel.rs:283-293).  The image is the
+    same bit for bit with and without; the device census shrinks (or stays) and still covers the reference's."""
+    ot, gs = _pair(orc, cuda, name)
+    cfg = fb.RenderConfig3D(size, size, size)
+    monkeypatch.setenv("FIDGET_B200_NO_CULL", "1")
+    plain, st_plain = fb.render3d(gs, cfg, stats=True)
+    monkeypatch.setenv("FIDGET_B200_NO_CULL", "0")
+    culled, st_cull = fb.render3d(gs, cfg, stats=True)
+    assert np.array_equal(plain.view(np.uint32), culled.view(np.uint32))
+    assert all(a <= b for a, b in zip(st_cull["evaluated"], st_plain["evaluated"]))
+    _, o_st = orc.render3d(ot, size, size, size, threads=8)
+    assert all(a >= b for a, b in zip(st_cull["evaluated"], o_st["evaluated"]))
+    if name == "bear.vm":
+        assert sum(st_cull["evaluated"]) < sum(st_plain["evaluated"])
