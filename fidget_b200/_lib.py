@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfidget_cuda.so")
+# FIDGET_B200_LIB: another build of the same library (A/B measurements of a kernel change on one box)
+LIB_PATH = os.environ.get("FIDGET_B200_LIB") or os.path.join(_HERE, "libfidget_cuda.so")
 _LIB = None
 
 
