@@ -50,48 +50,103 @@ struct Dec {
     }
 };
 
+// Dispatch of the f32 interpreters' hot loops: a 256-entry table (constant memory) maps the first byte of a clause
+// (opcode * 4 + form) to a dense handler number, so the switch below compiles to one jump table without range
+// compares, and each handler knows which operands are registers and which is the immediate (no per-component
+// selects on the form; the right-hand register is only loaded by the forms that read it).  Handlers exist for the
+// opcodes CSG tapes are made of; everything else is H_GENERIC.
+enum : uint32_t {
+    H_GENERIC = 0,
+    H_ADD_RR, H_ADD_RI, H_ADD_IR, H_SUB_RR, H_SUB_RI, H_SUB_IR, H_MUL_RR, H_MUL_RI, H_MUL_IR,
+    H_MIN_RR, H_MIN_RI, H_MIN_IR, H_MAX_RR, H_MAX_RI, H_MAX_IR,
+    H_NEG, H_ABS, H_SQRT, H_SQUARE, H_COPY_REG, H_COPY_IMM, H_COUNT
+};
+struct DopTable {
+    uint8_t h[256];
+};
+constexpr DopTable make_dop_table() {
+    DopTable t{};
+    for (int i = 0; i < 256; ++i) t.h[i] = H_GENERIC;
+    const uint32_t bin[5][2] = {{OP_ADD, H_ADD_RR}, {OP_SUB, H_SUB_RR}, {OP_MUL, H_MUL_RR}, {OP_MIN, H_MIN_RR}, {OP_MAX, H_MAX_RR}};
+    for (int k = 0; k < 5; ++k)
+        for (uint32_t f = 0; f < 3; ++f) t.h[bin[k][0] * 4u + f] = uint8_t(bin[k][1] + f);   // F_RR, F_RI, F_IR
+    t.h[OP_NEG * 4u + F_RR] = H_NEG;
+    t.h[OP_ABS * 4u + F_RR] = H_ABS;
+    t.h[OP_SQRT * 4u + F_RR] = H_SQRT;
+    t.h[OP_SQUARE * 4u + F_RR] = H_SQUARE;
+    t.h[OP_COPY * 4u + F_RR] = H_COPY_REG;
+    t.h[OP_COPY * 4u + F_ALIAS] = H_COPY_REG;
+    t.h[OP_COPY * 4u + F_RI] = H_COPY_IMM;
+    return t;
+}
+static __constant__ DopTable c_dop = make_dop_table();
+
 // ---------------------------------------------------------------------------
 // Interval interpreter.  `Input` maps a variable index to an interval,
 // `Sink` receives one choice per choice clause in evaluation order, `Out`
 // receives (output index, value).
+// Hot loop dispatched through c_dop like the f32 interpreters; both operand registers are still loaded before the
+// dispatch (a lone warp per parent tile: the loads' latency is the critical path, not their issue slots).
+#define FB_BINI(H, EXPR)                                                           \
+    case H##_RR: { const itv a = sl, b = sr; r = EXPR; break; }                    \
+    case H##_RI: { const itv a = sl, b = iv1(imm); r = EXPR; break; }              \
+    case H##_IR: { const itv a = iv1(imm), b = sr; r = EXPR; break; }
 template <bool NC = true, class Input, class Sink, class Out>
 __device__ __forceinline__ void run_interval(const uint2* __restrict__ tape, uint32_t n_ops, itv* slots,
                                              Input input, Sink& sink, Out out_fn) {
     if (n_ops == 0) return;
     uint2 w = ld_clause<NC>(tape);
     for (uint32_t i = 0; i < n_ops; ++i) {
-        uint2 nxt = ld_clause<NC>(tape + (i + 1 < n_ops ? i + 1 : i));
-        Dec d(w.x);
-        float imm = __uint_as_float(w.y);
-        itv sl = slots[d.lhs], sr = slots[d.rhs];
-        itv a = d.form == F_IR ? iv1(imm) : sl;
-        itv b = d.form == F_RI ? iv1(imm) : sr;
+        const uint2 nxt = ld_clause<NC>(tape + (i + 1 < n_ops ? i + 1 : i));
+        const uint32_t x = w.x;
+        const float imm = __uint_as_float(w.y);
+        const itv sl = slots[(x >> 16) & 0xffu], sr = slots[x >> 24];
         itv r;
-        if (d.op >= OP_MIN) {
-            if (d.op == OP_MEM) {
-                if (d.form == F_RI) slots[d.out] = slots[MEM_BASE + w.y];
-                else slots[MEM_BASE + w.y] = sl;
-                w = nxt;
-                continue;
+        uint32_t c = 0;   // 1 left, 2 right, 3 both for the choice opcodes
+        switch (c_dop.h[x & 0xffu]) {
+            FB_BINI(H_ADD, iv_add(a, b))
+            FB_BINI(H_SUB, iv_sub(a, b))
+            case H_MUL_RR: r = iv_mul(sl, sr); break;
+            case H_MUL_RI: r = iv_mul_f(sl, imm); break;
+            case H_MUL_IR: r = iv_mul(iv1(imm), sr); break;
+            FB_BINI(H_MIN, iv_choice_op(OP_MIN, a, b, c))
+            FB_BINI(H_MAX, iv_choice_op(OP_MAX, a, b, c))
+            case H_NEG: r = iv_neg(sl); break;
+            case H_ABS: r = iv_abs(sl); break;
+            case H_SQRT: r = iv_sqrt(sl); break;
+            case H_SQUARE: r = iv_square(sl); break;
+            case H_COPY_REG: r = sl; break;
+            case H_COPY_IMM: r = iv1(imm); break;
+            default: __builtin_unreachable();
+            case H_GENERIC: {
+                const Dec d(x);
+                const itv a = d.form == F_IR ? iv1(imm) : sl;
+                const itv b = d.form == F_RI ? iv1(imm) : sr;
+                if (d.op >= OP_MIN) {
+                    if (d.op == OP_MEM) {
+                        if (d.form == F_RI) slots[d.out] = slots[MEM_BASE + w.y];
+                        else slots[MEM_BASE + w.y] = sl;
+                        w = nxt;
+                        continue;
+                    }
+                    r = iv_choice_op(d.op, a, b, c);
+                } else if (d.op >= OP_ADD) {
+                    r = iv_binary(d.op, a, b);
+                } else if (d.op >= OP_NEG) {
+                    r = iv_unary(d.op, sl);
+                } else if (d.op == OP_INPUT) {
+                    r = input(w.y);
+                } else if (d.op == OP_OUTPUT) {
+                    out_fn(w.y, sl);
+                    w = nxt;
+                    continue;
+                } else {   // a COPY form without a handler
+                    r = d.form == F_RI ? iv1(imm) : sl;
+                }
             }
-            uint32_t c;
-            r = iv_choice_op(d.op, a, b, c);
-            sink.push(c);
-        } else if (d.op >= OP_ADD) {
-            if (d.op == OP_MUL && d.form == F_RI) r = iv_mul_f(sl, imm);
-            else r = iv_binary(d.op, a, b);
-        } else if (d.op >= OP_NEG) {
-            r = iv_unary(d.op, sl);
-        } else if (d.op == OP_COPY) {
-            r = d.form == F_RI ? iv1(imm) : sl;
-        } else if (d.op == OP_INPUT) {
-            r = input(w.y);
-        } else {  // OP_OUTPUT
-            out_fn(w.y, sl);
-            w = nxt;
-            continue;
         }
-        slots[d.out] = r;
+        if (c) sink.push(c);
+        slots[(x >> 8) & 0xffu] = r;
         w = nxt;
     }
 }
@@ -117,6 +172,11 @@ __device__ __forceinline__ float2 f32x2_binary(uint32_t op, float2 a, float2 b) 
     }
 }
 
+// Hot loop dispatched through c_dop (see above); H_GENERIC is the plain decode-and-select path.
+#define FB_BIN2(H, EXPR)                                                                     \
+    case H##_RR: { const float2 b = slots[x >> 24]; const float2 a = sl; r = EXPR; break; }  \
+    case H##_RI: { const float2 b = im; const float2 a = sl; r = EXPR; break; }              \
+    case H##_IR: { const float2 b = slots[x >> 24]; const float2 a = im; r = EXPR; break; }
 template <bool NC = true, class Input>
 __device__ __forceinline__ float2 run_f32x2(const uint2* __restrict__ tape, uint32_t n_ops, float2* slots,
                                             Input input) {
@@ -124,33 +184,52 @@ __device__ __forceinline__ float2 run_f32x2(const uint2* __restrict__ tape, uint
     if (n_ops == 0) return result;
     uint2 w = ld_clause<NC>(tape);
     for (uint32_t i = 0; i < n_ops; ++i) {
-        uint2 nxt = ld_clause<NC>(tape + (i + 1 < n_ops ? i + 1 : i));
-        Dec d(w.x);
-        float imm = __uint_as_float(w.y);
-        float2 sl = slots[d.lhs], sr = slots[d.rhs];
-        float2 a = d.form == F_IR ? make_float2(imm, imm) : sl;
-        float2 b = d.form == F_RI ? make_float2(imm, imm) : sr;
+        const uint2 nxt = ld_clause<NC>(tape + (i + 1 < n_ops ? i + 1 : i));
+        const uint32_t x = w.x;
+        const float imm = __uint_as_float(w.y);
+        const float2 sl = slots[(x >> 16) & 0xffu];
+        const float2 im = make_float2(imm, imm);
         float2 r;
-        if (d.op >= OP_ADD) {
-            if (d.op == OP_MEM) {
-                if (d.form == F_RI) slots[d.out] = slots[MEM_BASE + w.y];
-                else slots[MEM_BASE + w.y] = sl;
-                w = nxt;
-                continue;
+        switch (c_dop.h[x & 0xffu]) {
+            FB_BIN2(H_ADD, make_float2(a.x + b.x, a.y + b.y))
+            FB_BIN2(H_SUB, make_float2(a.x - b.x, a.y - b.y))
+            FB_BIN2(H_MUL, make_float2(a.x * b.x, a.y * b.y))
+            FB_BIN2(H_MIN, make_float2(f_min(a.x, b.x), f_min(a.y, b.y)))
+            FB_BIN2(H_MAX, make_float2(f_max(a.x, b.x), f_max(a.y, b.y)))
+            case H_NEG: r = make_float2(-sl.x, -sl.y); break;
+            case H_ABS: r = make_float2(fabsf(sl.x), fabsf(sl.y)); break;
+            case H_SQRT: r = make_float2(sqrtf(sl.x), sqrtf(sl.y)); break;
+            case H_SQUARE: r = make_float2(sl.x * sl.x, sl.y * sl.y); break;
+            case H_COPY_REG: r = sl; break;
+            case H_COPY_IMM: r = im; break;
+            default: __builtin_unreachable();
+            case H_GENERIC: {
+                const Dec d(x);
+                const float2 sr = slots[d.rhs];
+                const float2 a = d.form == F_IR ? im : sl;
+                const float2 b = d.form == F_RI ? im : sr;
+                if (d.op >= OP_ADD) {
+                    if (d.op == OP_MEM) {
+                        if (d.form == F_RI) slots[d.out] = slots[MEM_BASE + w.y];
+                        else slots[MEM_BASE + w.y] = sl;
+                        w = nxt;
+                        continue;
+                    }
+                    r = f32x2_binary(d.op, a, b);
+                } else if (d.op >= OP_NEG) {
+                    r = f32x2_unary(d.op, sl);
+                } else if (d.op == OP_COPY) {
+                    r = d.form == F_RI ? im : sl;
+                } else if (d.op == OP_INPUT) {
+                    r = input(w.y);
+                } else {
+                    if (w.y == 0) result = sl;
+                    w = nxt;
+                    continue;
+                }
             }
-            r = f32x2_binary(d.op, a, b);
-        } else if (d.op >= OP_NEG) {
-            r = f32x2_unary(d.op, sl);
-        } else if (d.op == OP_COPY) {
-            r = d.form == F_RI ? make_float2(imm, imm) : sl;
-        } else if (d.op == OP_INPUT) {
-            r = input(w.y);
-        } else {
-            if (w.y == 0) result = sl;
-            w = nxt;
-            continue;
         }
-        slots[d.out] = r;
+        slots[(x >> 8) & 0xffu] = r;
         w = nxt;
     }
     return result;
@@ -292,6 +371,11 @@ __device__ __forceinline__ float4 f32x4_binary(uint32_t op, float4 a, float4 b) 
                                     f32_binary(op, a.w, b.w));
     }
 }
+// Hot loop dispatched through c_dop (see above); H_GENERIC is the plain decode-and-select path.
+#define FB_BIN4(H, EXPR)                                                                     \
+    case H##_RR: { const float4 b = slots[x >> 24]; const float4 a = sl; r = EXPR; break; }  \
+    case H##_RI: { const float4 b = im; const float4 a = sl; r = EXPR; break; }              \
+    case H##_IR: { const float4 b = slots[x >> 24]; const float4 a = im; r = EXPR; break; }
 template <class Input>
 __device__ __forceinline__ float4 run_f32x4(const uint2* __restrict__ tape, uint32_t n_ops, float4* slots, Input input) {
     float4 result = make_float4(nanf_(), nanf_(), nanf_(), nanf_());
@@ -299,33 +383,51 @@ __device__ __forceinline__ float4 run_f32x4(const uint2* __restrict__ tape, uint
     uint2 w = __ldg(tape);
     for (uint32_t i = 0; i < n_ops; ++i) {
         const uint2 nxt = __ldg(tape + (i + 1 < n_ops ? i + 1 : i));
-        Dec d(w.x);
+        const uint32_t x = w.x;
         const float imm = __uint_as_float(w.y);
-        const float4 sl = slots[d.lhs], sr = slots[d.rhs];
+        const float4 sl = slots[(x >> 16) & 0xffu];
         const float4 im = make_float4(imm, imm, imm, imm);
-        const float4 a = d.form == F_IR ? im : sl;
-        const float4 b = d.form == F_RI ? im : sr;
         float4 r;
-        if (d.op >= OP_ADD) {
-            if (d.op == OP_MEM) {
-                if (d.form == F_RI) slots[d.out] = slots[MEM_BASE + w.y];
-                else slots[MEM_BASE + w.y] = sl;
-                w = nxt;
-                continue;
+        switch (c_dop.h[x & 0xffu]) {
+            FB_BIN4(H_ADD, make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w))
+            FB_BIN4(H_SUB, make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w))
+            FB_BIN4(H_MUL, make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w))
+            FB_BIN4(H_MIN, make_float4(f_min(a.x, b.x), f_min(a.y, b.y), f_min(a.z, b.z), f_min(a.w, b.w)))
+            FB_BIN4(H_MAX, make_float4(f_max(a.x, b.x), f_max(a.y, b.y), f_max(a.z, b.z), f_max(a.w, b.w)))
+            case H_NEG: r = make_float4(-sl.x, -sl.y, -sl.z, -sl.w); break;
+            case H_ABS: r = make_float4(fabsf(sl.x), fabsf(sl.y), fabsf(sl.z), fabsf(sl.w)); break;
+            case H_SQRT: r = make_float4(sqrtf(sl.x), sqrtf(sl.y), sqrtf(sl.z), sqrtf(sl.w)); break;
+            case H_SQUARE: r = make_float4(sl.x * sl.x, sl.y * sl.y, sl.z * sl.z, sl.w * sl.w); break;
+            case H_COPY_REG: r = sl; break;
+            case H_COPY_IMM: r = im; break;
+            default: __builtin_unreachable();
+            case H_GENERIC: {
+                const Dec d(x);
+                const float4 sr = slots[d.rhs];
+                const float4 a = d.form == F_IR ? im : sl;
+                const float4 b = d.form == F_RI ? im : sr;
+                if (d.op >= OP_ADD) {
+                    if (d.op == OP_MEM) {
+                        if (d.form == F_RI) slots[d.out] = slots[MEM_BASE + w.y];
+                        else slots[MEM_BASE + w.y] = sl;
+                        w = nxt;
+                        continue;
+                    }
+                    r = f32x4_binary(d.op, a, b);
+                } else if (d.op >= OP_NEG) {
+                    r = f32x4_unary(d.op, sl);
+                } else if (d.op == OP_COPY) {
+                    r = d.form == F_RI ? im : sl;
+                } else if (d.op == OP_INPUT) {
+                    r = input(w.y);
+                } else {
+                    if (w.y == 0) result = sl;
+                    w = nxt;
+                    continue;
+                }
             }
-            r = f32x4_binary(d.op, a, b);
-        } else if (d.op >= OP_NEG) {
-            r = f32x4_unary(d.op, sl);
-        } else if (d.op == OP_COPY) {
-            r = d.form == F_RI ? im : sl;
-        } else if (d.op == OP_INPUT) {
-            r = input(w.y);
-        } else {
-            if (w.y == 0) result = sl;
-            w = nxt;
-            continue;
         }
-        slots[d.out] = r;
+        slots[(x >> 8) & 0xffu] = r;
         w = nxt;
     }
     return result;
