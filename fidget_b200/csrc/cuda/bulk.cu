@@ -102,7 +102,37 @@ __global__ void __launch_bounds__(TMA_THREADS) k_slice_tma(const __grid_constant
             Dec d(w.x);
             const float imm = __uint_as_float(w.y);
             float4 r;
-            if (d.op == OP_INPUT) {
+            bool handled = false;
+            if (!GRAD) {
+                // the CSG opcodes go through the per-(opcode, form) handlers of interp.cuh's dispatch table
+                const uint32_t x = w.x;
+                const float4 im = make_float4(imm, imm, imm, imm);
+#define TMA_L my[size_t((x >> 16) & 0xffu) * TMA_THREADS]
+#define TMA_R my[size_t(x >> 24) * TMA_THREADS]
+#define TMA_BIN(H, EXPR)                                                                      \
+    case H##_RR: { const float4 a = TMA_L, b = TMA_R; r = EXPR; handled = true; break; }      \
+    case H##_RI: { const float4 a = TMA_L, b = im; r = EXPR; handled = true; break; }         \
+    case H##_IR: { const float4 a = im, b = TMA_R; r = EXPR; handled = true; break; }
+                switch (c_dop.h[x & 0xffu]) {
+                    TMA_BIN(H_ADD, make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w))
+                    TMA_BIN(H_SUB, make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w))
+                    TMA_BIN(H_MUL, make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w))
+                    TMA_BIN(H_MIN, make_float4(f_min(a.x, b.x), f_min(a.y, b.y), f_min(a.z, b.z), f_min(a.w, b.w)))
+                    TMA_BIN(H_MAX, make_float4(f_max(a.x, b.x), f_max(a.y, b.y), f_max(a.z, b.z), f_max(a.w, b.w)))
+                    case H_NEG: { const float4 a = TMA_L; r = make_float4(-a.x, -a.y, -a.z, -a.w); handled = true; break; }
+                    case H_ABS: { const float4 a = TMA_L; r = make_float4(fabsf(a.x), fabsf(a.y), fabsf(a.z), fabsf(a.w)); handled = true; break; }
+                    case H_SQRT: { const float4 a = TMA_L; r = make_float4(sqrtf(a.x), sqrtf(a.y), sqrtf(a.z), sqrtf(a.w)); handled = true; break; }
+                    case H_SQUARE: { const float4 a = TMA_L; r = make_float4(a.x * a.x, a.y * a.y, a.z * a.z, a.w * a.w); handled = true; break; }
+                    case H_COPY_REG: r = TMA_L; handled = true; break;
+                    case H_COPY_IMM: r = im; handled = true; break;
+                    default: break;
+                }
+#undef TMA_BIN
+#undef TMA_L
+#undef TMA_R
+            }
+            if (handled) {
+            } else if (d.op == OP_INPUT) {
                 r = in[size_t(w.y) * in_stride];
             } else if (d.op == OP_OUTPUT) {
                 const float4 v = my[size_t(d.lhs) * TMA_THREADS];

@@ -87,28 +87,46 @@ k_interval_root_coop(const __grid_constant__ LevelParams p) {
         };
         auto get_choice = [&](uint32_t cidx) { return (chs[cidx >> 4] >> ((cidx & 15u) * 2u)) & 3u; };
         auto exec = [&](const Fwd& rc, itv sl, itv sr) -> itv {
-            Dec d(rc.x);
-            float imm = __uint_as_float(rc.y);
-            itv a = d.form == F_IR ? iv1(imm) : sl;
-            itv b = d.form == F_RI ? iv1(imm) : sr;
+            // (records are sorted by their first byte inside a wave, so the lanes of a warp mostly share a handler)
+            const float imm = __uint_as_float(rc.y);
             itv r;
-            if (d.op >= OP_MIN) {
-                uint32_t c;
-                r = iv_choice_op(d.op, a, b, c);
-                put_choice(rc.cidx, c);
-            } else if (d.op >= OP_ADD) {
-                if (d.op == OP_MUL && d.form == F_RI) r = iv_mul_f(sl, imm);
-                else r = iv_binary(d.op, a, b);
-            } else if (d.op >= OP_NEG) {
-                r = iv_unary(d.op, sl);
-            } else if (d.op == OP_COPY) {
-                r = d.form == F_RI ? iv1(imm) : sl;
-            } else if (d.op == OP_INPUT) {
-                r = pick_input(p.vb, rc.y, vx, vy, vz, [](float f) { return iv1(f); });
-            } else {
-                if (rc.y == 0) s_res = sl;
-                r = sl;
+            uint32_t c = 0;
+            switch (c_dop.h[rc.x & 0xffu]) {
+                FB_BINI(H_ADD, iv_add(a, b))
+                FB_BINI(H_SUB, iv_sub(a, b))
+                case H_MUL_RR: r = iv_mul(sl, sr); break;
+                case H_MUL_RI: r = iv_mul_f(sl, imm); break;
+                case H_MUL_IR: r = iv_mul(iv1(imm), sr); break;
+                FB_BINI(H_MIN, iv_choice_op(OP_MIN, a, b, c))
+                FB_BINI(H_MAX, iv_choice_op(OP_MAX, a, b, c))
+                case H_NEG: r = iv_neg(sl); break;
+                case H_ABS: r = iv_abs(sl); break;
+                case H_SQRT: r = iv_sqrt(sl); break;
+                case H_SQUARE: r = iv_square(sl); break;
+                case H_COPY_REG: r = sl; break;
+                case H_COPY_IMM: r = iv1(imm); break;
+                default: __builtin_unreachable();
+                case H_GENERIC: {
+                    const Dec d(rc.x);
+                    const itv a = d.form == F_IR ? iv1(imm) : sl;
+                    const itv b = d.form == F_RI ? iv1(imm) : sr;
+                    if (d.op >= OP_MIN) {
+                        r = iv_choice_op(d.op, a, b, c);
+                    } else if (d.op >= OP_ADD) {
+                        r = iv_binary(d.op, a, b);
+                    } else if (d.op >= OP_NEG) {
+                        r = iv_unary(d.op, sl);
+                    } else if (d.op == OP_COPY) {
+                        r = d.form == F_RI ? iv1(imm) : sl;
+                    } else if (d.op == OP_INPUT) {
+                        r = pick_input(p.vb, rc.y, vx, vy, vz, [](float f) { return iv1(f); });
+                    } else {
+                        if (rc.y == 0) s_res = sl;
+                        r = sl;
+                    }
+                }
             }
+            if (c) put_choice(rc.cidx, c);
             return r;
         };
         auto ld = [&](uint32_t id) { return id != COOP_NONE ? vals[id] : iv_nan(); };
