@@ -59,27 +59,32 @@ enum : uint32_t {
     H_GENERIC = 0,
     H_ADD_RR, H_ADD_RI, H_ADD_IR, H_SUB_RR, H_SUB_RI, H_SUB_IR, H_MUL_RR, H_MUL_RI, H_MUL_IR,
     H_MIN_RR, H_MIN_RI, H_MIN_IR, H_MAX_RR, H_MAX_RI, H_MAX_IR,
-    H_NEG, H_ABS, H_SQRT, H_SQUARE, H_COPY_REG, H_COPY_IMM, H_COUNT
+    H_NEG, H_ABS, H_SQRT, H_SQUARE, H_COPY_REG, H_COPY_IMM,
+    H_DIV_RR, H_DIV_RI, H_DIV_IR, H_EXP,   // c_dop_f only (bear.vm's other frequent opcodes)
+    H_COUNT
 };
 struct DopTable {
     uint8_t h[256];
 };
-constexpr DopTable make_dop_table() {
+constexpr DopTable make_dop_table(bool f32) {
     DopTable t{};
     for (int i = 0; i < 256; ++i) t.h[i] = H_GENERIC;
-    const uint32_t bin[5][2] = {{OP_ADD, H_ADD_RR}, {OP_SUB, H_SUB_RR}, {OP_MUL, H_MUL_RR}, {OP_MIN, H_MIN_RR}, {OP_MAX, H_MAX_RR}};
-    for (int k = 0; k < 5; ++k)
+    const uint32_t bin[6][2] = {{OP_ADD, H_ADD_RR}, {OP_SUB, H_SUB_RR}, {OP_MUL, H_MUL_RR}, {OP_MIN, H_MIN_RR}, {OP_MAX, H_MAX_RR},
+                                {OP_DIV, H_DIV_RR}};
+    for (int k = 0; k < (f32 ? 6 : 5); ++k)
         for (uint32_t f = 0; f < 3; ++f) t.h[bin[k][0] * 4u + f] = uint8_t(bin[k][1] + f);   // F_RR, F_RI, F_IR
     t.h[OP_NEG * 4u + F_RR] = H_NEG;
     t.h[OP_ABS * 4u + F_RR] = H_ABS;
     t.h[OP_SQRT * 4u + F_RR] = H_SQRT;
     t.h[OP_SQUARE * 4u + F_RR] = H_SQUARE;
+    if (f32) t.h[OP_EXP * 4u + F_RR] = H_EXP;
     t.h[OP_COPY * 4u + F_RR] = H_COPY_REG;
     t.h[OP_COPY * 4u + F_ALIAS] = H_COPY_REG;
     t.h[OP_COPY * 4u + F_RI] = H_COPY_IMM;
     return t;
 }
-static __constant__ DopTable c_dop = make_dop_table();
+static __constant__ DopTable c_dop = make_dop_table(false);     // interval interpreters
+static __constant__ DopTable c_dop_f = make_dop_table(true);    // f32 interpreters: + div, exp
 
 // ---------------------------------------------------------------------------
 // Interval interpreter.  `Input` maps a variable index to an interval,
@@ -190,7 +195,7 @@ __device__ __forceinline__ float2 run_f32x2(const uint2* __restrict__ tape, uint
         const float2 sl = slots[(x >> 16) & 0xffu];
         const float2 im = make_float2(imm, imm);
         float2 r;
-        switch (c_dop.h[x & 0xffu]) {
+        switch (c_dop_f.h[x & 0xffu]) {
             FB_BIN2(H_ADD, make_float2(a.x + b.x, a.y + b.y))
             FB_BIN2(H_SUB, make_float2(a.x - b.x, a.y - b.y))
             FB_BIN2(H_MUL, make_float2(a.x * b.x, a.y * b.y))
@@ -202,6 +207,8 @@ __device__ __forceinline__ float2 run_f32x2(const uint2* __restrict__ tape, uint
             case H_SQUARE: r = make_float2(sl.x * sl.x, sl.y * sl.y); break;
             case H_COPY_REG: r = sl; break;
             case H_COPY_IMM: r = im; break;
+            FB_BIN2(H_DIV, make_float2(a.x / b.x, a.y / b.y))
+            case H_EXP: r = make_float2(expf(sl.x), expf(sl.y)); break;
             default: __builtin_unreachable();
             case H_GENERIC: {
                 const Dec d(x);
@@ -357,7 +364,22 @@ __device__ __forceinline__ float4 f32x4_unary(uint32_t op, float4 a) {
         case OP_ABS: return make_float4(fabsf(a.x), fabsf(a.y), fabsf(a.z), fabsf(a.w));
         case OP_SQRT: return make_float4(sqrtf(a.x), sqrtf(a.y), sqrtf(a.z), sqrtf(a.w));
         case OP_SQUARE: return make_float4(a.x * a.x, a.y * a.y, a.z * a.z, a.w * a.w);
-        default: return make_float4(f32_unary(op, a.x), f32_unary(op, a.y), f32_unary(op, a.z), f32_unary(op, a.w));
+        default: {
+#ifndef FIDGET_UNROLLED_COLD
+            // the long opcodes (libdevice transcendentals, rounding, rand ...) once in the code, not once per component:
+            // the leaf kernels are instruction-cache sensitive (div and exp, frequent in bear.vm, have handlers of their own)
+            float4 r = a;
+#pragma unroll 1
+            for (int k = 0; k < 4; ++k) {
+                const float t = f32_unary(op, a.x);
+                a = make_float4(a.y, a.z, a.w, a.x);
+                r = make_float4(r.y, r.z, r.w, t);
+            }
+            return r;
+#else
+            return make_float4(f32_unary(op, a.x), f32_unary(op, a.y), f32_unary(op, a.z), f32_unary(op, a.w));
+#endif
+        }
     }
 }
 __device__ __forceinline__ float4 f32x4_binary(uint32_t op, float4 a, float4 b) {
@@ -367,8 +389,22 @@ __device__ __forceinline__ float4 f32x4_binary(uint32_t op, float4 a, float4 b) 
         case OP_MUL: return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
         case OP_MIN: return make_float4(f_min(a.x, b.x), f_min(a.y, b.y), f_min(a.z, b.z), f_min(a.w, b.w));
         case OP_MAX: return make_float4(f_max(a.x, b.x), f_max(a.y, b.y), f_max(a.z, b.z), f_max(a.w, b.w));
-        default: return make_float4(f32_binary(op, a.x, b.x), f32_binary(op, a.y, b.y), f32_binary(op, a.z, b.z),
-                                    f32_binary(op, a.w, b.w));
+        default: {
+#ifndef FIDGET_UNROLLED_COLD
+            float4 r = a;
+#pragma unroll 1
+            for (int k = 0; k < 4; ++k) {
+                const float t = f32_binary(op, a.x, b.x);
+                a = make_float4(a.y, a.z, a.w, a.x);
+                b = make_float4(b.y, b.z, b.w, b.x);
+                r = make_float4(r.y, r.z, r.w, t);
+            }
+            return r;
+#else
+            return make_float4(f32_binary(op, a.x, b.x), f32_binary(op, a.y, b.y), f32_binary(op, a.z, b.z),
+                               f32_binary(op, a.w, b.w));
+#endif
+        }
     }
 }
 // Hot loop dispatched through c_dop (see above); H_GENERIC is the plain decode-and-select path.
@@ -388,7 +424,7 @@ __device__ __forceinline__ float4 run_f32x4(const uint2* __restrict__ tape, uint
         const float4 sl = slots[(x >> 16) & 0xffu];
         const float4 im = make_float4(imm, imm, imm, imm);
         float4 r;
-        switch (c_dop.h[x & 0xffu]) {
+        switch (c_dop_f.h[x & 0xffu]) {
             FB_BIN4(H_ADD, make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w))
             FB_BIN4(H_SUB, make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w))
             FB_BIN4(H_MUL, make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w))
@@ -400,6 +436,8 @@ __device__ __forceinline__ float4 run_f32x4(const uint2* __restrict__ tape, uint
             case H_SQUARE: r = make_float4(sl.x * sl.x, sl.y * sl.y, sl.z * sl.z, sl.w * sl.w); break;
             case H_COPY_REG: r = sl; break;
             case H_COPY_IMM: r = im; break;
+            FB_BIN4(H_DIV, make_float4(a.x / b.x, a.y / b.y, a.z / b.z, a.w / b.w))
+            case H_EXP: r = make_float4(expf(sl.x), expf(sl.y), expf(sl.z), expf(sl.w)); break;
             default: __builtin_unreachable();
             case H_GENERIC: {
                 const Dec d(x);
