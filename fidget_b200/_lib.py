@@ -100,6 +100,7 @@ FC_FLAG_TIMING = 2
 FC_FLAG_NO_CLAMP = 4
 FC_FLAG_FUSED_TAIL = 8
 FC_FLAG_EXACT_CENSUS = 16
+FC_FLAG_FULL_LADDER = 32
 FC_OUT_F32, FC_OUT_MASK_U8, FC_OUT_BITMAP_1BIT, FC_OUT_RGBA8 = 0, 1, 2, 3
 
 # name -> (restype, argtypes); mirrors include/fidget_cuda.h one to one

@@ -369,6 +369,21 @@ int32_t fc_render3d(fc_ctx* c, const fc_tape* tape, const fc_render3d_cfg* cfg, 
     std::vector<uint32_t> ts;
     int32_t rc = pick_tile_sizes(cfg->tile_sizes, cfg->n_tile_sizes, DFLT, 5, std::max(cfg->width, cfg->height), ts);
     if (rc) return rc;
+    if (cfg->n_tile_sizes == 0 && !(cfg->flags & (FC_FLAG_FULL_LADDER | FC_FLAG_EXACT_CENSUS)) &&
+        !env_int("FIDGET_B200_FULL_LADDER", 0)) {
+        // Device ladder: every other size of the default one.  A warp then carries 32 children per pass instead of 8
+        // and a whole level of launches, job records and tape writes disappears; the image cannot change, because a
+        // child's interval result on its grandparent's tape equals the one on its parent's simplified tape (a choice
+        // the parent's region decided is decided the same way on any sub-region, and the pruned branch never
+        // contributed to the value) -- tests/test_gpu_parity.py compares the two ladders bit for bit.
+        std::vector<uint32_t> fused(1, ts[0]);
+        for (size_t i = 0; i + 1 < ts.size();) {
+            const size_t nx = std::min(i + 2, ts.size() - 1);
+            fused.push_back(ts[nx]);
+            i = nx;
+        }
+        ts.swap(fused);
+    }
     const int L = int(ts.size());
     const uint32_t T0 = ts[0];
     const uint32_t roots_x = (cfg->width + T0 - 1) / T0, roots_y_all = (cfg->height + T0 - 1) / T0;

@@ -357,6 +357,7 @@ class RenderConfig3D:
     clamp: bool = True                          # False for slab renders (fc_merge_slabs applies it)
     interleave: tuple = (0, 0)                  # (N, r): only the root-tile columns rank r of N owns
     exact_census: bool = False                  # stats = the reference's front-to-back census (voxel.rs:244-357)
+    full_ladder: bool = False                   # default tile sizes: evaluate all of (128,64,32,16,8), not the device's (128,32,8)
 
     def matrix(self):
         return self.mat if self.mat is not None else voxel_mat(self.width, self.height, self.depth,
@@ -411,7 +412,8 @@ def render3d(shape: CudaShape, cfg: RenderConfig3D, out=None, stats: bool = Fals
     for i, t in enumerate(cfg.tile_sizes):
         c.tile_sizes[i] = t
     c.flags = (_lib.FC_FLAG_TIMING if cfg.timing else 0) | (_lib.FC_FLAG_ASYNC if asynchronous else 0) | \
-        (0 if cfg.clamp else _lib.FC_FLAG_NO_CLAMP) | (_lib.FC_FLAG_EXACT_CENSUS if cfg.exact_census else 0)
+        (0 if cfg.clamp else _lib.FC_FLAG_NO_CLAMP) | (_lib.FC_FLAG_EXACT_CENSUS if cfg.exact_census else 0) | \
+        (_lib.FC_FLAG_FULL_LADDER if cfg.full_ladder else 0)
     c.z_begin, c.z_end = cfg.z_range
     c.root_row_begin, c.root_row_end = cfg.root_rows
     c.root_stride, c.root_offset = cfg.interleave

@@ -151,6 +151,12 @@ int32_t fc_simplify(fc_eval* e, const fc_tape* parent, const uint8_t* choices, s
                                    walk (voxel.rs:244-357), computed from the final heightmap; without it the census counts what
                                    the device evaluated (a superset: it only culls whole parents behind interval-proven tiles).  Whole-volume renders of
                                    images whose sides are multiples of the root tile */
+#define FC_FLAG_FULL_LADDER 32u /* fc_render3d with the default tile sizes: evaluate every size of the reference's ladder
+                                   {128,64,32,16,8}.  Without it the device skips every other size ({128,32,8}: a 4x4x4 split
+                                   evaluated with the parent's tape, as fidget-wgpu's interval_tiles.wgsl does) -- the image is
+                                   the same bit for bit (interval results of a sub-region never contradict its parent's
+                                   choices), 7-10 % faster, and fc_render_stats then describes those three levels.
+                                   FC_FLAG_EXACT_CENSUS implies the full ladder; explicit tile_sizes are always used as given */
 #define FC_FLAG_NO_CLAMP 4u     /* fc_render3d: skip the final depth clamp (slab renders; fc_merge_slabs applies it) */
 
 #define FC_OUT_F32 0u          /* width*height RawDistancePixel bits as f32 (pixel::render's own output) */

@@ -774,8 +774,8 @@ def test_render3d_exact_census_matches_the_reference_walk(orc, cuda, name, size)
     for k in ("evaluated", "filled_inside", "filled_outside", "ambiguous", "simplified"):
         assert g_st[k] == o_st[k], (k, g_st[k], o_st[k])
     assert g_st["pixels"] == o_st["pixels"]
-    # without the flag the census is what the device evaluated: a superset
-    _, raw = fb.render3d(gs, fb.RenderConfig3D(size, size, size), stats=True)
+    # without the flag the census is what the device evaluated: a superset (on the same ladder of tile sizes)
+    _, raw = fb.render3d(gs, fb.RenderConfig3D(size, size, size, full_ladder=True), stats=True)
     assert all(a >= b for a, b in zip(raw["evaluated"], o_st["evaluated"]))
     with pytest.raises(fb.CudaError):
         fb.render3d(gs, fb.RenderConfig3D(100, 100, 100, exact_census=True), stats=True)
@@ -787,7 +787,7 @@ def test_render3d_occlusion_culling_changes_nothing_but_the_work(orc, cuda, name
     tiles) are skipped, like the reference's front-to-back walk skips them (voxel.rs:283-293).  The image is the
     same bit for bit with and without; the device census shrinks (or stays) and still covers the reference's."""
     ot, gs = _pair(orc, cuda, name)
-    cfg = fb.RenderConfig3D(size, size, size)
+    cfg = fb.RenderConfig3D(size, size, size, full_ladder=True)
     monkeypatch.setenv("FIDGET_B200_NO_CULL", "1")
     plain, st_plain = fb.render3d(gs, cfg, stats=True)
     monkeypatch.setenv("FIDGET_B200_NO_CULL", "0")
@@ -798,3 +798,23 @@ def test_render3d_occlusion_culling_changes_nothing_but_the_work(orc, cuda, name
     assert all(a >= b for a, b in zip(st_cull["evaluated"], o_st["evaluated"]))
     if name == "bear.vm":
         assert sum(st_cull["evaluated"]) < sum(st_plain["evaluated"])
+
+
+@pytest.mark.parametrize("name,size", [("prospero.vm", 512), ("bear.vm", 512), ("colonnade.vm", 256), ("tanglecube.vm", 256),
+                                       ("hi.vm", 128), ("prospero.vm", 200)])
+def test_render3d_device_ladder_gives_the_reference_ladders_image(cuda, name, size, models):
+    """With the default tile sizes the device evaluates (128, 32, 8) instead of the reference's (128, 64, 32, 16, 8):
+    a 4 x 4 x 4 split on the parent's tape.  Depth and normals are the same bit for bit (a choice decided on a region
+    is decided the same way on every sub-region, and the pruned branch never contributed to the value), also with an
+    explicit mixed ladder; only the census describes different levels.  (The slab, band and interleave tests run on
+    the device ladder; the full-size tests compare it with the oracle's reference ladder.)"""
+    gs = fb.CudaShape.from_vm(cuda, models(name))
+    full, st_full = fb.render3d(gs, fb.RenderConfig3D(size, size, size, full_ladder=True), stats=True)
+    dev, st_dev = fb.render3d(gs, fb.RenderConfig3D(size, size, size), stats=True)
+    assert np.array_equal(full.view(np.uint32), dev.view(np.uint32))
+    assert st_dev["evaluated"][0] == st_full["evaluated"][0] and st_dev["pixels"] == pytest.approx(st_full["pixels"], rel=0.02)
+    n_full = sum(1 for e in st_full["evaluated"] if e)
+    n_dev = sum(1 for e in st_dev["evaluated"] if e)
+    assert n_dev < n_full or n_full <= 2
+    explicit = fb.render3d(gs, fb.RenderConfig3D(size, size, size, tile_sizes=(128, 64, 16, 8)))
+    assert np.array_equal(full.view(np.uint32), explicit.view(np.uint32))
