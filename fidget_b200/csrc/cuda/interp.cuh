@@ -472,29 +472,58 @@ __device__ __forceinline__ float4 run_f32x4(const uint2* __restrict__ tape, uint
 }
 
 // Gradient interpreter (VmGradSliceEval, vm/mod.rs:1097-1396)
+#define FB_BING(H, EXPR)                                                                  \
+    case H##_RR: { const grd a = sl, b = slots[x >> 24]; r = EXPR; break; }               \
+    case H##_RI: { const grd a = sl, b = gr1(imm); r = EXPR; break; }                     \
+    case H##_IR: { const grd a = gr1(imm), b = slots[x >> 24]; r = EXPR; break; }
 template <class Input>
 __device__ __forceinline__ grd run_grad(const uint2* __restrict__ tape, uint32_t n_ops, grd* slots, Input input) {
     grd result = gr1(nanf_());
     for (uint32_t i = 0; i < n_ops; ++i) {
         const uint2 w = __ldg(tape + i);
-        Dec d(w.x);
+        const uint32_t x = w.x;
         const float imm = __uint_as_float(w.y);
-        const grd sl = slots[d.lhs], sr = slots[d.rhs];
-        const grd a = d.form == F_IR ? gr1(imm) : sl;
-        const grd b = d.form == F_RI ? gr1(imm) : sr;
+        const grd sl = slots[(x >> 16) & 0xffu];
         grd r;
-        if (d.op == OP_MEM) {
-            if (d.form == F_RI) slots[d.out] = slots[MEM_BASE + w.y];
-            else slots[MEM_BASE + w.y] = sl;
-            continue;
-        } else if (d.op >= OP_ADD) {
-            if (d.op == OP_MUL && d.form == F_RI) r = gr_mul_f(sl, imm);
-            else r = gr_binary(d.op, a, b);
-        } else if (d.op >= OP_NEG) r = gr_unary(d.op, sl);
-        else if (d.op == OP_COPY) r = d.form == F_RI ? gr1(imm) : sl;
-        else if (d.op == OP_INPUT) r = input(w.y);
-        else { if (w.y == 0) result = sl; continue; }
-        slots[d.out] = r;
+        switch (c_dop_f.h[x & 0xffu]) {
+            FB_BING(H_ADD, gr_add(a, b))
+            FB_BING(H_SUB, gr_sub(a, b))
+            case H_MUL_RR: r = gr_mul(sl, slots[x >> 24]); break;
+            case H_MUL_RI: r = gr_mul_f(sl, imm); break;
+            case H_MUL_IR: r = gr_mul(gr1(imm), slots[x >> 24]); break;
+            FB_BING(H_MIN, gr_binary(OP_MIN, a, b))
+            FB_BING(H_MAX, gr_binary(OP_MAX, a, b))
+            FB_BING(H_DIV, gr_div(a, b))
+            case H_NEG: r = gr_neg(sl); break;
+            case H_SQUARE: r = gr_mul(sl, sl); break;
+            case H_COPY_REG: r = sl; break;
+            case H_COPY_IMM: r = gr1(imm); break;
+            default: __builtin_unreachable();
+            case H_ABS: case H_SQRT: case H_EXP:
+            case H_GENERIC: {
+                const Dec d(x);
+                const grd sr = slots[d.rhs];
+                const grd a = d.form == F_IR ? gr1(imm) : sl;
+                const grd b = d.form == F_RI ? gr1(imm) : sr;
+                if (d.op == OP_MEM) {
+                    if (d.form == F_RI) slots[d.out] = slots[MEM_BASE + w.y];
+                    else slots[MEM_BASE + w.y] = sl;
+                    continue;
+                } else if (d.op >= OP_ADD) {
+                    r = gr_binary(d.op, a, b);
+                } else if (d.op >= OP_NEG) {
+                    r = gr_unary(d.op, sl);
+                } else if (d.op == OP_COPY) {
+                    r = d.form == F_RI ? gr1(imm) : sl;
+                } else if (d.op == OP_INPUT) {
+                    r = input(w.y);
+                } else {
+                    if (w.y == 0) result = sl;
+                    continue;
+                }
+            }
+        }
+        slots[(x >> 8) & 0xffu] = r;
     }
     return result;
 }
