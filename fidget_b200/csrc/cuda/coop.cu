@@ -260,8 +260,10 @@ k_interval_root_coop(const __grid_constant__ LevelParams p) {
                 if (x < p.width && y < p.height) atomicMax(&p.heightmap[size_t(y) * p.width + x], key);
             }
             if (p.occl && T % 16u == 0u)
-                for (uint32_t q = tid; q < (T / 16u) * (T / 16u); q += NT)
-                    atomicMax(p.occl + size_t(cy / 16u + q / (T / 16u)) * p.occl_w + cx / 16u + q % (T / 16u), cz + T + 1u);
+                for (uint32_t q = tid; q < (T / 16u) * (T / 16u); q += NT) {
+                    const uint32_t bx = cx / 16u + q % (T / 16u), by = cy / 16u + q / (T / 16u);
+                    if (bx < p.occl_w && by < p.occl_h) atomicMax(p.occl + size_t(by) * p.occl_w + bx, cz + T + 1u);
+                }
         }
         if (tid == 0) {
             if (DIM == 2 && !amb) {

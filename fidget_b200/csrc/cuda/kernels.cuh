@@ -153,7 +153,7 @@ struct LevelParams {
     // (raised by interval-proven-inside tiles that cover whole blocks).  A parent whose blocks all reach its top + 1
     // cannot show anything: its children are skipped (cull != 0: this level's parents are made of whole blocks).
     uint32_t* occl;
-    uint32_t occl_w;                // blocks per row
+    uint32_t occl_w, occl_h;        // blocks per row, block rows (tiles may overhang a ragged image: blocks outside are skipped)
     uint32_t cull;
     CensusRec* census;              // exact 3D census records (or null)
     uint32_t cap_census;

@@ -61,8 +61,10 @@ __device__ __forceinline__ void level_job(const LevelParams& p, uint32_t j, uint
             // tiles in its front-to-back walk (voxel.rs:283-293) -- and more, since it also knows the voxel hits in
             // front, which arrive last here.  One small read of the occlusion map per lane, not the heightmap itself.
             const uint32_t nb = (T * p.n_axis) / 16u, need = pz + T * p.n_axis + 1u;   // blocks per side of the parent
-            for (uint32_t q = lane; q < nb * nb; q += 32u)
-                cull_open |= __ldcg(p.occl + size_t(py / 16u + q / nb) * p.occl_w + px / 16u + q % nb) < need;
+            for (uint32_t q = lane; q < nb * nb; q += 32u) {
+                const uint32_t bx = px / 16u + q % nb, by = py / 16u + q / nb;
+                if (bx < p.occl_w && by < p.occl_h) cull_open |= __ldcg(p.occl + size_t(by) * p.occl_w + bx) < need;
+            }
             cull_check = true;
         }
     }
@@ -130,8 +132,10 @@ __device__ __forceinline__ void level_job(const LevelParams& p, uint32_t j, uint
                     if (x < p.width && y < p.height) atomicMax(&p.heightmap[size_t(y) * p.width + x], key);
                 }
                 if (p.occl && T % 16u == 0u)   // the whole blocks this tile covers now hold its depth (the same value the heightmap gets)
-                    for (uint32_t q = lane; q < (T / 16u) * (T / 16u); q += 32u)
-                        atomicMax(p.occl + size_t(fy / 16u + q / (T / 16u)) * p.occl_w + fx / 16u + q % (T / 16u), fz + T + 1u);
+                    for (uint32_t q = lane; q < (T / 16u) * (T / 16u); q += 32u) {
+                        const uint32_t bx = fx / 16u + q % (T / 16u), by = fy / 16u + q / (T / 16u);
+                        if (bx < p.occl_w && by < p.occl_h) atomicMax(p.occl + size_t(by) * p.occl_w + bx, fz + T + 1u);
+                    }
             }
             if (p.stats) {
                 uint32_t mv = __ballot_sync(FULL, valid), mi = __ballot_sync(FULL, fill_in),

@@ -501,6 +501,7 @@ int32_t fc_render3d(fc_ctx* c, const fc_tape* tape, const fc_render3d_cfg* cfg, 
         p.heightmap = c->heightmap.as<unsigned long long>();
         p.occl = use_occl ? c->occl.as<uint32_t>() : nullptr;
         p.occl_w = occl_w;
+        p.occl_h = occl_h;
         p.cull = (use_occl && l >= 1 && ts[l - 1] >= 16u && ts[l - 1] <= 64u) ? 1u : 0u;   // parents made of 1, 4 or 16 blocks
         p.census = exact_census ? c->census.as<CensusRec>() : nullptr;
         p.cap_census = uint32_t(cap_census);

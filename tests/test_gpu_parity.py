@@ -818,3 +818,27 @@ def test_render3d_device_ladder_gives_the_reference_ladders_image(cuda, name, si
     assert n_dev < n_full or n_full <= 2
     explicit = fb.render3d(gs, fb.RenderConfig3D(size, size, size, tile_sizes=(128, 64, 16, 8)))
     assert np.array_equal(full.view(np.uint32), explicit.view(np.uint32))
+
+
+def _edge_slab_and_ball(Ctx):
+    """Inside for x > 0.9 and z > 0.3 (a slab hugging the right edge, in front), plus a small ball at the left, behind."""
+    ctx = Ctx()
+    x, y, z = ctx.x(), ctx.y(), ctx.z()
+    slab = ctx.max(ctx.sub(ctx.constant(0.9), x), ctx.sub(ctx.constant(0.3), z))
+    dx, dy, dz = ctx.add(x, ctx.constant(0.85)), ctx.sub(y, ctx.constant(0.1)), ctx.add(z, ctx.constant(0.5))
+    ball = ctx.sub(ctx.sqrt(ctx.add(ctx.add(ctx.square(dx), ctx.square(dy)), ctx.square(dz))), ctx.constant(0.12))
+    return ctx.tape(ctx.min(slab, ball))
+
+
+@pytest.mark.parametrize("size", [(100, 100, 100), (140, 100, 120), (172, 172, 100), (104, 104, 72)])
+@pytest.mark.parametrize("full_ladder", [False, True])
+def test_render3d_ragged_image_with_full_tiles_hanging_over_the_edge(orc, cuda, size, full_ladder):
+    """Interval-proven tiles that overhang the right / bottom edge of a ragged image must not touch occlusion blocks
+    outside it (an unchecked block column wraps into the next block row and would cull the ball at the left)."""
+    w, h, d = size
+    ot = orc.Tape.from_data(_edge_slab_and_ball(orc.Context))
+    gs = fb.CudaShape(cuda, _edge_slab_and_ball(fb.Context))
+    o_img, _ = orc.render3d(ot, w, h, d, threads=8)
+    g_img = fb.render3d(gs, fb.RenderConfig3D(w, h, d, full_ladder=full_ladder))
+    _cmp3d(g_img, o_img, exact_normals=True)
+    assert (o_img["depth"][:, : w // 4] > 0).any()        # the ball is in the picture
