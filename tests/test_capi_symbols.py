@@ -106,3 +106,26 @@ def test_generated_rust_binding_is_current():
     rs = open(os.path.join(ROOT, "bindings", "rust", "ffi.rs")).read()
     for name in declared("include/fidget_cuda.h", "fc_"):
         assert f"pub fn {name}(" in rs, name
+
+
+def test_python_constants_mirror_the_header_defines():
+    """Every FC_FLAG_* / FC_OUT_* / FC_ERR_* / FC_ABI_VERSION #define of include/fidget_cuda.h that the ctypes face
+    names carries the header's value (a flag added on one side only would silently select another behaviour)."""
+    import re
+    from fidget_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "include", "fidget_cuda.h")) as f:
+        text = f.read()
+    defines = {m.group(1): int(m.group(2).rstrip("uU"), 0)
+               for m in re.finditer(r"^#define\s+(FC_[A-Z0-9_]+)\s+(-?(?:0x[0-9a-fA-F]+|\d+)[uU]?)\b", text, re.M)}
+    flags = {k: v for k, v in defines.items() if k.startswith("FC_FLAG_")}
+    assert len(flags) >= 6 and len(set(flags.values())) == len(flags)           # distinct bits
+    assert all(v & (v - 1) == 0 for v in flags.values())
+    checked = 0
+    for name, value in defines.items():
+        if hasattr(_lib, name):
+            assert getattr(_lib, name) == value, name
+            checked += 1
+    assert checked >= 10
+    for name in flags:                                                            # every flag is reachable from Python
+        assert hasattr(_lib, name), name
