@@ -109,3 +109,33 @@ def test_the_independent_evaluator_knows_every_opcode_the_models_use():
             if len(parts) >= 2:
                 used.add(parts[1])
     assert used <= set(UNARY) | set(BINARY) | {"const", "var-x", "var-y", "var-z"}
+
+
+@pytest.mark.parametrize("name", IEEE_MODELS + LIBM_MODELS)
+def test_interval_results_enclose_the_text_evaluated_inside_the_box(orc, name):
+    """Soundness of the interval path of the register tape against the same independent reading: for random boxes the
+    interval the VM returns contains the function's value at points sampled inside the box (small slack for the VM's
+    round-to-nearest interval arithmetic)."""
+    text = model_text(name)
+    t = orc.Tape.from_vm(text)
+    slots = t.data.var_slots()
+    rng = np.random.default_rng(3)
+    checked = 0
+    for _ in range(60 if name == "prospero.vm" else 150):
+        centre = rng.uniform(-1, 1, 3)
+        half = rng.choice([0.5, 0.1, 0.02]) * rng.uniform(0.2, 1.0, 3)
+        lo, hi = (centre - half).astype(np.float32), (centre + half).astype(np.float32)
+        box = np.zeros((t.n_vars, 2), dtype=np.float32)
+        for axis, slot in enumerate(slots):
+            if slot >= 0:
+                box[slot] = (lo[axis], hi[axis])
+        (out_lo, out_hi), _, _ = t.interval_eval(box)
+        if np.isnan(out_lo) or np.isnan(out_hi):
+            continue                                   # the VM gave up on this box (e.g. sqrt of a straddling interval)
+        pts = [rng.uniform(lo[k], hi[k], 64).astype(np.float32) for k in range(3)]
+        vals = eval_vm_text(text, *pts)
+        vals = vals[np.isfinite(vals)]
+        slack = 1e-5 * max(1.0, abs(float(out_lo)), abs(float(out_hi)))
+        assert (vals >= out_lo - slack).all() and (vals <= out_hi + slack).all(), (name, lo, hi, out_lo, out_hi)
+        checked += 1
+    assert checked >= 30
