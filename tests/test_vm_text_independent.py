@@ -139,3 +139,50 @@ def test_interval_results_enclose_the_text_evaluated_inside_the_box(orc, name):
         assert (vals >= out_lo - slack).all() and (vals <= out_hi + slack).all(), (name, lo, hi, out_lo, out_hi)
         checked += 1
     assert checked >= 30
+
+
+@pytest.mark.parametrize("name", IEEE_MODELS)
+def test_simplified_tapes_still_compute_the_text_inside_their_box(orc, name):
+    """VmData::simplify through the independent reading: a tape simplified with the choices of a box (and once more
+    with those of a sub-box) returns, at points inside, exactly what the full text returns -- bit for bit -- and never
+    grows."""
+    text = model_text(name)
+    t = orc.Tape.from_vm(text)
+    slots = t.data.var_slots()
+    rng = np.random.default_rng(9)
+
+    def box_of(lo, hi):
+        b = np.zeros((t.n_vars, 2), dtype=np.float32)
+        for axis, slot in enumerate(slots):
+            if slot >= 0:
+                b[slot] = (lo[axis], hi[axis])
+        return b
+
+    def inputs_of(pts):
+        ins = [None] * t.n_vars
+        for axis, slot in enumerate(slots):
+            if slot >= 0:
+                ins[slot] = pts[axis]
+        return ins
+
+    shrunk = 0
+    for _ in range(25 if name == "prospero.vm" else 60):
+        centre = rng.uniform(-0.9, 0.9, 3)
+        half = rng.choice([0.25, 0.06]) * rng.uniform(0.3, 1.0, 3)
+        lo, hi = (centre - half).astype(np.float32), (centre + half).astype(np.float32)
+        _, choices, can = t.interval_eval(box_of(lo, hi))
+        child = t.simplify(choices) if can else t
+        assert child.size <= t.size
+        # a sub-box, simplified from the child
+        lo2, hi2 = (centre - half / 4).astype(np.float32), (centre + half / 4).astype(np.float32)
+        _, choices2, can2 = child.interval_eval(box_of(lo2, hi2))
+        grandchild = child.simplify(choices2) if can2 else child
+        assert grandchild.size <= child.size
+        shrunk += grandchild.size < t.size
+        pts = [rng.uniform(lo2[k], hi2[k], 256).astype(np.float32) for k in range(3)]
+        want = eval_vm_text(text, *pts)
+        for tape in (child, grandchild):
+            got = tape.float_slice_eval(inputs_of(pts))
+            both_nan = np.isnan(want) & np.isnan(got)
+            assert np.array_equal(want.view(np.uint32)[~both_nan], got.view(np.uint32)[~both_nan])
+    assert shrunk > 0 or t.choice_count == 0          # tanglecube has no min / max: nothing to prune
