@@ -186,3 +186,23 @@ def test_simplified_tapes_still_compute_the_text_inside_their_box(orc, name):
             both_nan = np.isnan(want) & np.isnan(got)
             assert np.array_equal(want.view(np.uint32)[~both_nan], got.view(np.uint32)[~both_nan])
     assert shrunk > 0 or t.choice_count == 0          # tanglecube has no min / max: nothing to prune
+
+
+@pytest.mark.parametrize("name,size", [("hi.vm", 96), ("quarter.vm", 96), ("prospero.vm", 128)])
+def test_rendered_image_is_the_text_evaluated_at_every_pixel(orc, name, size):
+    """The whole chain -- text -> front end -> register tape -> tile recursion, interval proofs, chained simplification,
+    leaf evaluation -- against the independent reading at every pixel's model-space point: same sign everywhere, same
+    bits wherever the renderer shaded a pixel instead of filling a proven tile."""
+    from test_oracle_bruteforce import model_points
+    text = model_text(name)
+    t = orc.Tape.from_vm(text)
+    img, st = orc.render2d(t, size, size, tile_sizes=(32, 8))
+    ys, xs = np.mgrid[0:size, 0:size]
+    pts = model_points(orc, orc.pixel_mat(size, size), xs.ravel(), ys.ravel(), np.zeros(size * size))
+    want = eval_vm_text(text, np.ascontiguousarray(pts[:, 0]), np.ascontiguousarray(pts[:, 1]),
+                        np.ascontiguousarray(pts[:, 2])).reshape(size, size)
+    bits = img.view(np.uint32)
+    is_fill = np.isnan(img) & ((bits & np.uint32(0xFF << 9)) == np.uint32(0xF6 << 9))
+    assert np.array_equal(orc.pixel_inside(img), want < 0)
+    assert np.array_equal(img.view(np.uint32)[~is_fill], want.view(np.uint32)[~is_fill])
+    assert is_fill.sum() + st["pixels"] == size * size and st["pixels"] > 0
